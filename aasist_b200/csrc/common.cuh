@@ -1,0 +1,182 @@
+// Shared definitions for libaasist_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/aasist_b200.h"
+
+namespace aasist {
+
+constexpr float kSeluAlpha = 1.6732632423543772f;
+constexpr float kSeluScale = 1.0507009873554805f;
+constexpr double kBnEps = 1e-5;
+constexpr int kSpecNodes = 23;  // pooled sinc bands == spectral graph nodes (AASIST.py:774)
+
+__device__ __forceinline__ float selu(float v) {
+  // torch SELU: scale * (max(0,x) + min(0, alpha*(exp(x)-1)))
+  return v > 0.f ? kSeluScale * v : (kSeluScale * kSeluAlpha) * expm1f(v);
+}
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define AASIST_CUDA(expr)                                   \
+  do {                                                      \
+    cudaError_t _e = (expr);                                \
+    if (_e != cudaSuccess) return cuda_fail(_e, #expr);     \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------
+// packed parameters
+// ---------------------------------------------------------------------------------------
+struct ConvBlockF32 {  // one Residual_block, fp32 CUDA-core path
+  int ci = 0, co = 0;
+  bool downsample = false;
+  float* w1 = nullptr;  // [ci][2][3][co]  conv1 with bn2 folded
+  float* b1 = nullptr;  // [co]
+  float* w2 = nullptr;  // [co][2][3][co]
+  float* b2 = nullptr;  // [co]  conv2 bias (+ conv_downsample bias)
+  float* wd = nullptr;  // [ci][3][co]     conv_downsample (k(1,3)) or null
+};
+
+struct GatParams {  // GraphAttentionLayer (AASIST.py:17-110), eval BN folded into the projections
+  int D, Do;
+  const float* attWt;  // [D][Do]  att_proj.weight^T
+  const float* attB;   // [Do]
+  const float* attW;   // [Do]     att_weight
+  const float* pWt;    // [D][Do]  proj_with_att.weight^T    * bn_scale
+  const float* qWt;    // [D][Do]  proj_without_att.weight^T * bn_scale
+  const float* bias;   // [Do]     (b_with + b_without - bn_mean) * bn_scale + bn_bias
+  float temp;
+};
+
+struct HtrgParams {  // HtrgGraphAttentionLayer (AASIST.py:113-282)
+  int D, Do;
+  const float *t1Wt, *t1B, *t2Wt, *t2B;   // proj_type1/2: [D][D], [D]
+  const float *attWt, *attB;              // att_proj
+  const float *w11, *w22, *w12;           // att_weight11/22/12 [Do]
+  const float *attMWt, *attMB, *wM;       // att_projM, att_weightM
+  const float *pWt, *qWt, *bias;          // node projection, BN folded
+  const float *pMWt, *qMWt, *biasM;       // master projection (no BN): bias = b_withM + b_withoutM
+  float temp;
+};
+
+struct PoolParams {  // GraphPool (AASIST.py:285-322)
+  int D;
+  const float* w;  // [D]
+  float b;
+};
+
+struct GraphArgsAasist {
+  // dims
+  int C, NT, g0, g1, nS, nT, nS2, nT2;
+  int ld;            // smem row stride (floats), odd
+  int nmax;          // max node count of any layer
+  const float* e;    // (B,C,23,NT)
+  const float* posS; // (23,C)
+  const float *master1, *master2;  // (g0)
+  GatParams gatS, gatT;
+  HtrgParams st11, st12, st21, st22;
+  PoolParams poolS, poolT, poolhS1, poolhT1, poolhS2, poolhT2;
+  const float* outWt;  // [5*g1][2]
+  float outB0, outB1;
+  float* last_hidden;  // (B,5*g1)
+  float* logits;       // (B,2)
+  int32_t* topk_idx;   // (B,topk_total) or null
+  float* pool_scores;  // (B,score_total) or null
+  int topk_total, score_total;
+};
+
+struct GraphArgsRawGat {
+  int NT;            // temporal nodes of encoder_S output (29)
+  int ld, nmax;
+  const float* eT;   // encoder_T output (B,64,23,NT) -> 23 nodes (max over time)
+  const float* eS;   // encoder_S output (B,64,23,NT) -> NT nodes (max over freq)
+  GatParams gatT, gatS, gatST;
+  PoolParams poolT, poolS, poolST;
+  int nT, nS, nST;   // pooled node counts (14, 23, 7)
+  const float *projTW, *projTB;   // Linear(14,12): [12][14], [12]
+  const float *projSW, *projSB;   // Linear(23,12): [12][23], [12]
+  const float* projSTW; float projSTB;  // Linear(16,1)
+  const float *outW, *outB;       // Linear(7,2): [2][7], [2]
+  float* last_hidden;  // (B,7)
+  float* logits;
+  int32_t* topk_idx;
+  float* pool_scores;
+  int topk_total, score_total;
+};
+
+struct TcState;  // tensor-core path state (encoder_tc.cu)
+
+}  // namespace aasist
+
+struct aasist_handle {
+  aasist_config cfg;
+  int device = 0;
+  int taps = 129;
+  bool finalized = false;
+  int64_t launches = 0;
+  std::vector<std::pair<std::string, int64_t>> expected;     // strict state_dict layout
+  std::map<std::string, std::vector<float>> params;          // host copies
+  // device-side packed state
+  float* bank = nullptr;                 // (n_filters, taps)
+  float bn0_scale = 1.f, bn0_shift = 0.f;  // first_bn folded to y = scale*p + shift
+  aasist::ConvBlockF32 blocks[2][6];     // [encoder][block]
+  int n_encoders = 1;
+  float* graph_buf = nullptr;            // all packed graph parameters
+  std::vector<float> graph_host;         // staging while packing
+  aasist::GraphArgsAasist ga;            // pointers filled at finalize (io pointers per call)
+  aasist::GraphArgsRawGat gr;
+  aasist::TcState* tc = nullptr;
+  // per-kernel event timing (aasist_profile_*)
+  bool profiling = false;
+  struct ProfSpan { const char* name; cudaEvent_t a, b; };
+  std::vector<ProfSpan> prof_pending;
+  std::vector<cudaEvent_t> prof_pool;
+  std::map<std::string, std::pair<int64_t, double>> prof_totals;
+  // pinned staging for aasist_forward_host
+  float* pin_x = nullptr; size_t pin_x_bytes = 0;
+  float* pin_out = nullptr; size_t pin_out_bytes = 0;
+  void* dev_stage = nullptr; size_t dev_stage_bytes = 0;
+};
+
+namespace aasist {
+// RAII span around one kernel launch: counts it and, when profiling, brackets it with events.
+struct LaunchSpan {
+  aasist_handle* h;
+  cudaStream_t st;
+  int idx = -1;
+  LaunchSpan(aasist_handle* h_, const char* name, cudaStream_t st_) : h(h_), st(st_) {
+    h->launches++;
+    if (!h->profiling) return;
+    auto get = [&]() {
+      cudaEvent_t e;
+      if (!h->prof_pool.empty()) { e = h->prof_pool.back(); h->prof_pool.pop_back(); }
+      else cudaEventCreate(&e);
+      return e;
+    };
+    aasist_handle::ProfSpan sp{name, get(), get()};
+    cudaEventRecord(sp.a, st);
+    h->prof_pending.push_back(sp);
+    idx = (int)h->prof_pending.size() - 1;
+  }
+  ~LaunchSpan() {
+    if (idx >= 0) cudaEventRecord(h->prof_pending[idx].b, st);
+  }
+};
+// kernels' host launchers (each returns 0 / AASIST_E_*; counts launches into h->launches)
+int build_filterbank(aasist_handle* h);
+int launch_frontend_f32(aasist_handle* h, const float* x, int B, int L, float* out, cudaStream_t st);
+int launch_block_f32(aasist_handle* h, const ConvBlockF32& blk, const float* in, int B, int W,
+                     float* mid, float* out, cudaStream_t st);
+int launch_graph_aasist(aasist_handle* h, const float* e, int B, int NT, float* last_hidden,
+                        float* logits, int32_t* topk, float* scores, cudaStream_t st);
+int launch_graph_rawgat(aasist_handle* h, const float* eT, const float* eS, int B, int NT,
+                        float* last_hidden, float* logits, int32_t* topk, float* scores,
+                        cudaStream_t st);
+int pooled_count(int n, double ratio, int min_nodes);
+}  // namespace aasist

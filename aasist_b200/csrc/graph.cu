@@ -1,0 +1,584 @@
+// Graph module: everything after the encoder, one CTA per utterance, node features in shared
+// memory, fp32 throughout (accurate tanhf/expf: GraphPool indices must match the reference).
+//   a5  node extraction                 models/AASIST.py:841-842,848-849
+//   a6  GraphAttentionLayer             models/AASIST.py:43-110
+//   a7  GraphPool (sigmoid, top-k)      models/AASIST.py:294-322
+//   a8  HtrgGraphAttentionLayer         models/AASIST.py:150-282
+//   a9  branch fusion, readout, head    models/AASIST.py:865-921
+//   a11 RawGAT-ST graph tail            models/RawNetGatSpoofST.py:338-356
+#include "common.cuh"
+
+namespace aasist {
+
+constexpr int kGraphThreads = 256;
+constexpr int kWarps = kGraphThreads / 32;
+constexpr int kMaxDim = 64;          // max feature width of any graph layer
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+struct Scratch {
+  float* Wst;    // [kMaxDim][kMaxDim] staged attention projection (transposed, padded to Dop)
+  float* vb;     // staged attB
+  float* va;     // staged att weight (type 11 / plain)
+  float* vb2;    // staged att weight 22
+  float* vc;     // staged att weight 12
+  float* A;      // [nmax][lda] attention logits / map
+  int lda;
+  float* AGG;    // [nmax][ld]
+  float* sc;     // [nmax] pool scores (sigmoid)
+  float* wts;    // [nmax] pool weights (pre-sigmoid) / master logits
+  int* idx;      // [nmax]
+  float* aggM;   // [kMaxDim]
+};
+
+// ---- attention logits over all unordered node pairs (the map is symmetric) --------------
+// A[i][j] = A[j][i] = (w_type . tanh(W_att (x_i * x_j) + b_att)) / temp
+// one lane per pair, 8 output dims at a time; weights broadcast from shared memory.
+__device__ void att_logits(const float* X, int N, int ld, int D, int Do, const float* attWt,
+                           const float* attB, const float* w11, const float* w22,
+                           const float* w12, int n1, float temp, const Scratch& S) {
+  const int Dop = (Do + 7) & ~7;
+  for (int i = threadIdx.x; i < D * Dop; i += kGraphThreads) {
+    int d = i / Dop, k = i % Dop;
+    S.Wst[i] = k < Do ? attWt[d * Do + k] : 0.f;
+  }
+  for (int k = threadIdx.x; k < Dop; k += kGraphThreads) {
+    bool ok = k < Do;
+    S.vb[k] = ok ? attB[k] : 0.f;
+    S.va[k] = ok ? w11[k] : 0.f;
+    S.vb2[k] = ok ? w22[k] : 0.f;
+    S.vc[k] = ok ? w12[k] : 0.f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int pairs = N * (N + 1) / 2;
+  for (int base = warp * 32; base < pairs; base += kWarps * 32) {
+    int p = base + lane;
+    bool valid = p < pairs;
+    if (!valid) p = 0;
+    // decode p -> (i, j), i <= j, row-major upper triangle; start(i) = i*(2N-i+1)/2
+    float fn = (float)(2 * N + 1);
+    int i = (int)((fn - sqrtf(fn * fn - 8.f * (float)p)) * 0.5f);
+    i = max(0, min(i, N - 1));
+    while (i + 1 < N && (i + 1) * (2 * N - i) / 2 <= p) ++i;
+    while (i > 0 && i * (2 * N - i + 1) / 2 > p) --i;
+    int j = i + (p - i * (2 * N - i + 1) / 2);
+    const float* xi = X + i * ld;
+    const float* xj = X + j * ld;
+    const float* wsel = (j < n1) ? S.va : ((i >= n1) ? S.vb2 : S.vc);
+    float logit = 0.f;
+    for (int kg = 0; kg < Dop; kg += 8) {
+      float pre[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) pre[q] = S.vb[kg + q];
+#pragma unroll 4
+      for (int d = 0; d < D; ++d) {
+        float pr = xi[d] * xj[d];
+        const float4 wa = *reinterpret_cast<const float4*>(S.Wst + d * Dop + kg);
+        const float4 wb = *reinterpret_cast<const float4*>(S.Wst + d * Dop + kg + 4);
+        pre[0] = fmaf(pr, wa.x, pre[0]); pre[1] = fmaf(pr, wa.y, pre[1]);
+        pre[2] = fmaf(pr, wa.z, pre[2]); pre[3] = fmaf(pr, wa.w, pre[3]);
+        pre[4] = fmaf(pr, wb.x, pre[4]); pre[5] = fmaf(pr, wb.y, pre[5]);
+        pre[6] = fmaf(pr, wb.z, pre[6]); pre[7] = fmaf(pr, wb.w, pre[7]);
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) logit = fmaf(wsel[kg + q], tanhf(pre[q]), logit);
+    }
+    logit = logit / temp;
+    if (valid) {
+      S.A[i * S.lda + j] = logit;
+      S.A[j * S.lda + i] = logit;
+    }
+  }
+  __syncthreads();
+}
+
+// softmax over j of every row i (F.softmax(att_map, dim=-2), AASIST.py:89)
+__device__ void softmax_rows(int N, const Scratch& S) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = warp; i < N; i += kWarps) {
+    float* row = S.A + i * S.lda;
+    float m = -INFINITY;
+    for (int j = lane; j < N; j += 32) m = fmaxf(m, row[j]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int j = lane; j < N; j += 32) {
+      float e = expf(row[j] - m);
+      row[j] = e;
+      s += e;
+    }
+    s = warp_sum(s);
+    for (int j = lane; j < N; j += 32) row[j] = row[j] / s;
+  }
+  __syncthreads();
+}
+
+// AGG[i][:] = sum_j A[i][j] X[j][:]     (torch.matmul(att_map.squeeze(-1), x), AASIST.py:94)
+__device__ void aggregate(const float* X, int N, int ld, int D, const Scratch& S) {
+  for (int t = threadIdx.x; t < N * D; t += kGraphThreads) {
+    int i = t / D, d = t % D;
+    const float* a = S.A + i * S.lda;
+    float s = 0.f;
+    for (int j = 0; j < N; ++j) s = fmaf(a[j], X[j * ld + d], s);
+    S.AGG[i * ld + d] = s;
+  }
+  __syncthreads();
+}
+
+// OUT[i][k] = act(bias[k] + sum_d Wt[d][k] IN[i][d] (+ sum_d W2t[d][k] IN2[i][d]))
+// rows [r0, r0+n) of IN/IN2/OUT; weights in global memory (coalesced over k, L1/L2 resident).
+template <bool SELU>
+__device__ void linear_rows(const float* IN, const float* IN2, int n, int ldin, int D,
+                            const float* Wt, const float* W2t, const float* bias, int Do,
+                            float* OUT, int ldout) {
+  const int nblk = (n + 3) / 4;
+  for (int t = threadIdx.x; t < nblk * Do; t += kGraphThreads) {
+    int k = t % Do, i0 = (t / Do) * 4;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    int r[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) r[q] = min(i0 + q, n - 1) * ldin;
+#pragma unroll 4
+    for (int d = 0; d < D; ++d) {
+      float w = __ldg(Wt + d * Do + k);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q] = fmaf(w, IN[r[q] + d], acc[q]);
+      if (IN2) {
+        float w2 = __ldg(W2t + d * Do + k);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q] = fmaf(w2, IN2[r[q] + d], acc[q]);
+      }
+    }
+    float bk = __ldg(bias + k);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (i0 + q < n) {
+        float v = acc[q] + bk;
+        OUT[(i0 + q) * ldout + k] = SELU ? selu(v) : v;
+      }
+  }
+  __syncthreads();
+}
+
+// GraphAttentionLayer.forward (AASIST.py:43-59): X (N,D) -> OUT (N,Do)
+__device__ void gat_layer(const float* X, int N, int ld, const GatParams& P, float* OUT,
+                          const Scratch& S) {
+  att_logits(X, N, ld, P.D, P.Do, P.attWt, P.attB, P.attW, P.attW, P.attW, N, P.temp, S);
+  softmax_rows(N, S);
+  aggregate(X, N, ld, P.D, S);
+  linear_rows<true>(S.AGG, X, N, ld, P.D, P.pWt, P.qWt, P.bias, P.Do, OUT, ld);
+}
+
+// HtrgGraphAttentionLayer.forward (AASIST.py:150-185).
+// X1 (n1,D) temporal, X2 (n2,D) spectral, m_in (D)  ->  OUT rows [0,n1) / [n1,n1+n2), m_out (Do)
+// HX: scratch (n1+n2, D) for the type-projected nodes.
+__device__ void htrg_layer(const float* X1, int n1, const float* X2, int n2, int ld,
+                           const float* m_in, const HtrgParams& P, float* HX, float* OUT,
+                           float* m_out, const Scratch& S) {
+  const int N = n1 + n2, D = P.D, Do = P.Do;
+  linear_rows<false>(X1, nullptr, n1, ld, D, P.t1Wt, nullptr, P.t1B, D, HX, ld);              // :158
+  linear_rows<false>(X2, nullptr, n2, ld, D, P.t2Wt, nullptr, P.t2B, D, HX + n1 * ld, ld);    // :159
+  att_logits(HX, N, ld, D, Do, P.attWt, P.attB, P.w11, P.w22, P.w12, n1, P.temp, S);          // :225-251
+  softmax_rows(N, S);                                                                        // :253
+  // master attention (AASIST.py:208-223): lm[j] = wM . tanh(W_M (x_j * m) + b_M) / temp
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int j = warp; j < N; j += kWarps) {
+      float part = 0.f;
+      for (int k = lane; k < Do; k += 32) {
+        float pre = __ldg(P.attMB + k);
+        for (int d = 0; d < D; ++d)
+          pre = fmaf(HX[j * ld + d] * m_in[d], __ldg(P.attMWt + d * Do + k), pre);
+        part = fmaf(__ldg(P.wM + k), tanhf(pre), part);
+      }
+      part = warp_sum(part);
+      if (lane == 0) S.wts[j] = part / P.temp;
+    }
+    __syncthreads();
+    if (warp == 0) {  // softmax over nodes
+      float m = -INFINITY;
+      for (int j = lane; j < N; j += 32) m = fmaxf(m, S.wts[j]);
+      m = warp_max(m);
+      float s = 0.f;
+      for (int j = lane; j < N; j += 32) {
+        float e = expf(S.wts[j] - m);
+        S.wts[j] = e;
+        s += e;
+      }
+      s = warp_sum(s);
+      for (int j = lane; j < N; j += 32) S.wts[j] = S.wts[j] / s;
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < D; d += kGraphThreads) {
+      float s = 0.f;
+      for (int j = 0; j < N; ++j) s = fmaf(S.wts[j], HX[j * ld + d], s);
+      S.aggM[d] = s;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < Do; k += kGraphThreads) {                                   // :263-269
+      float a = 0.f, b = 0.f;
+      for (int d = 0; d < D; ++d) {
+        a = fmaf(__ldg(P.pMWt + d * Do + k), S.aggM[d], a);
+        b = fmaf(__ldg(P.qMWt + d * Do + k), m_in[d], b);
+      }
+      m_out[k] = a + b + __ldg(P.biasM + k);
+    }
+    __syncthreads();
+  }
+  aggregate(HX, N, ld, D, S);                                                                 // :258
+  linear_rows<true>(S.AGG, HX, N, ld, D, P.pWt, P.qWt, P.bias, Do, OUT, ld);                 // :257-261,179-180
+}
+
+// GraphPool.forward (AASIST.py:294-322): H (N,D) -> OUT (k,D) in descending score order.
+// Exact score ties go to the lower node index (torch leaves that order unspecified).
+__device__ void graph_pool(const float* H, int N, int ld, const PoolParams& P, int k, float* OUT,
+                           int32_t* g_idx, float* g_wts, const Scratch& S) {
+  for (int i = threadIdx.x; i < N; i += kGraphThreads) {
+    float w = 0.f;
+    for (int d = 0; d < P.D; ++d) w = fmaf(__ldg(P.w + d), H[i * ld + d], w);
+    w += P.b;
+    S.wts[i] = w;
+    S.sc[i] = 1.f / (1.f + expf(-w));
+    if (g_wts) g_wts[i] = w;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < N; i += kGraphThreads) {
+    float si = S.sc[i];
+    int r = 0;
+    for (int j = 0; j < N; ++j) {
+      float sj = S.sc[j];
+      r += (sj > si) || (sj == si && j < i);
+    }
+    if (r < k) {
+      S.idx[r] = i;
+      if (g_idx) g_idx[r] = i;
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < k * P.D; t += kGraphThreads) {
+    int r = t / P.D, d = t % P.D;
+    int i = S.idx[r];
+    OUT[r * ld + d] = H[i * ld + d] * S.sc[i];
+  }
+  __syncthreads();
+}
+
+// spectral nodes: X[f][c] = max_t |e[c][f][t]| (+ pos[f][c]);  temporal: X[t][c] = max_f |e[c][f][t]|
+__device__ void nodes_max_over_time(const float* e, int C, int NT, const float* pos, float* X,
+                                    int ld) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int r = warp; r < C * kSpecNodes; r += kWarps) {
+    int c = r / kSpecNodes, f = r % kSpecNodes;
+    const float* row = e + (size_t)r * NT;
+    float m = 0.f;
+    for (int t = lane; t < NT; t += 32) m = fmaxf(m, fabsf(row[t]));
+    m = warp_max(m);
+    if (lane == 0) X[f * ld + c] = m + (pos ? __ldg(pos + f * C + c) : 0.f);
+  }
+  __syncthreads();
+}
+__device__ void nodes_max_over_freq(const float* e, int C, int NT, float* X, int ld) {
+  for (int i = threadIdx.x; i < C * NT; i += kGraphThreads) {
+    int c = i / NT, t = i % NT;
+    const float* col = e + (size_t)c * kSpecNodes * NT + t;
+    float m = 0.f;
+    for (int f = 0; f < kSpecNodes; ++f) m = fmaxf(m, fabsf(col[f * NT]));
+    X[t * ld + c] = m;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ float* bump(float*& p, int n) {
+  float* r = p;
+  p += (n + 3) & ~3;
+  return r;
+}
+
+__host__ __device__ inline int scratch_floats(int nmax) {
+  int lda = nmax + 1;
+  return kMaxDim * kMaxDim + 4 * kMaxDim + ((nmax * lda + 3) & ~3) + 3 * ((nmax + 3) & ~3) + kMaxDim;
+}
+
+__device__ void carve_scratch(float*& p, int nmax, int ld, Scratch& S) {
+  S.Wst = bump(p, kMaxDim * kMaxDim);
+  S.vb = bump(p, kMaxDim);
+  S.va = bump(p, kMaxDim);
+  S.vb2 = bump(p, kMaxDim);
+  S.vc = bump(p, kMaxDim);
+  S.lda = nmax + 1;
+  S.A = bump(p, nmax * S.lda);
+  S.sc = bump(p, nmax);
+  S.wts = bump(p, nmax);
+  S.idx = reinterpret_cast<int*>(bump(p, nmax));
+  S.aggM = bump(p, kMaxDim);
+  S.AGG = nullptr;
+}
+
+// ---------------------------------------------------------------------------------------
+// AASIST graph tail (AASIST.py:841-921)
+// ---------------------------------------------------------------------------------------
+__host__ __device__ inline int aasist_graph_smem_floats(int nmax, int ld, int nS, int nT, int nS2,
+                                                        int nT2) {
+  int rows = 3 * nmax + (nT2 + nS2) + nS + nT + (nT2 + nS2);
+  return scratch_floats(nmax) + rows * ld + 4 * kMaxDim + 64;
+}
+
+__global__ void __launch_bounds__(kGraphThreads)
+aasist_graph_kernel(const GraphArgsAasist a) {
+  extern __shared__ __align__(16) float smem[];
+  float* p = smem;
+  Scratch S;
+  carve_scratch(p, a.nmax, a.ld, S);
+  const int ld = a.ld;
+  float* B0 = bump(p, a.nmax * ld);
+  float* B1 = bump(p, a.nmax * ld);
+  S.AGG = bump(p, a.nmax * ld);
+  float* B3 = bump(p, (a.nT2 + a.nS2) * ld);     // pooled hetero nodes: T rows then S rows
+  float* OS = bump(p, a.nS * ld);
+  float* OT = bump(p, a.nT * ld);
+  float* R = bump(p, (a.nT2 + a.nS2) * ld);      // branch-1 result: T rows then S rows
+  float* Rm = bump(p, kMaxDim);
+  float* m1 = bump(p, kMaxDim);
+  float* m2 = bump(p, kMaxDim);
+  float* m0 = bump(p, kMaxDim);
+
+  const int b = blockIdx.x;
+  const float* e = a.e + (size_t)b * a.C * kSpecNodes * a.NT;
+  int32_t* gi = a.topk_idx ? a.topk_idx + (size_t)b * a.topk_total : nullptr;
+  float* gw = a.pool_scores ? a.pool_scores + (size_t)b * a.score_total : nullptr;
+
+  // spectral graph                                                       (AASIST.py:841-845)
+  nodes_max_over_time(e, a.C, a.NT, a.posS, B0, ld);
+  gat_layer(B0, kSpecNodes, ld, a.gatS, B1, S);
+  graph_pool(B1, kSpecNodes, ld, a.poolS, a.nS, OS, gi, gw, S);
+  if (gi) gi += a.nS;
+  if (gw) gw += kSpecNodes;
+  // temporal graph                                                       (AASIST.py:848-852)
+  nodes_max_over_freq(e, a.C, a.NT, B0, ld);
+  gat_layer(B0, a.NT, ld, a.gatT, B1, S);
+  graph_pool(B1, a.NT, ld, a.poolT, a.nT, OT, gi, gw, S);
+  if (gi) gi += a.nT;
+  if (gw) gw += a.NT;
+
+  float* PT = B3;
+  float* PS = B3 + a.nT2 * ld;
+  for (int br = 0; br < 2; ++br) {                                       // :859-869 / :872-881
+    const HtrgParams& L1 = br == 0 ? a.st11 : a.st21;
+    const HtrgParams& L2 = br == 0 ? a.st12 : a.st22;
+    const PoolParams& pS = br == 0 ? a.poolhS1 : a.poolhS2;
+    const PoolParams& pT = br == 0 ? a.poolhT1 : a.poolhT2;
+    for (int d = threadIdx.x; d < a.g0; d += kGraphThreads)
+      m0[d] = __ldg((br == 0 ? a.master1 : a.master2) + d);
+    __syncthreads();
+    htrg_layer(OT, a.nT, OS, a.nS, ld, m0, L1, B0, B1, m1, S);
+    graph_pool(B1 + a.nT * ld, a.nS, ld, pS, a.nS2, PS, gi, gw, S);      // pool_hS first (:862)
+    if (gi) gi += a.nS2;
+    if (gw) gw += a.nS;
+    graph_pool(B1, a.nT, ld, pT, a.nT2, PT, gi, gw, S);
+    if (gi) gi += a.nT2;
+    if (gw) gw += a.nT;
+    htrg_layer(PT, a.nT2, PS, a.nS2, ld, m1, L2, B0, B1, m2, S);
+    // residual adds (:867-869) and branch-wise max (:890-892)
+    const int n2 = a.nT2 + a.nS2;
+    for (int t = threadIdx.x; t < n2 * a.g1; t += kGraphThreads) {
+      int r = t / a.g1, k = t % a.g1;
+      float v = B3[r * ld + k] + B1[r * ld + k];
+      R[r * ld + k] = br == 0 ? v : fmaxf(R[r * ld + k], v);
+    }
+    for (int k = threadIdx.x; k < a.g1; k += kGraphThreads) {
+      float v = m1[k] + m2[k];
+      Rm[k] = br == 0 ? v : fmaxf(Rm[k], v);
+    }
+    __syncthreads();
+  }
+  // readout (:903-910) + output layer (:919)
+  float* lh = S.AGG;  // reuse: 5*g1 floats
+  const int g1 = a.g1;
+  for (int k = threadIdx.x; k < g1; k += kGraphThreads) {
+    float tmax = 0.f, tsum = 0.f, smax = 0.f, ssum = 0.f;
+    for (int r = 0; r < a.nT2; ++r) {
+      float v = R[r * ld + k];
+      tmax = fmaxf(tmax, fabsf(v));
+      tsum += v;
+    }
+    for (int r = 0; r < a.nS2; ++r) {
+      float v = R[(a.nT2 + r) * ld + k];
+      smax = fmaxf(smax, fabsf(v));
+      ssum += v;
+    }
+    lh[k] = tmax;
+    lh[g1 + k] = tsum / (float)a.nT2;
+    lh[2 * g1 + k] = smax;
+    lh[3 * g1 + k] = ssum / (float)a.nS2;
+    lh[4 * g1 + k] = Rm[k];
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < 5 * g1; k += kGraphThreads)
+    a.last_hidden[(size_t)b * 5 * g1 + k] = lh[k];
+  if (threadIdx.x < 64) {
+    const int lane = threadIdx.x & 31, o = threadIdx.x >> 5;
+    float s = 0.f;
+    for (int k = lane; k < 5 * g1; k += 32) s = fmaf(lh[k], __ldg(a.outWt + k * 2 + o), s);
+    s = warp_sum(s);
+    if (lane == 0) a.logits[(size_t)b * 2 + o] = s + (o == 0 ? a.outB0 : a.outB1);
+  }
+}
+
+int launch_graph_aasist(aasist_handle* h, const float* e, int B, int NT, float* last_hidden,
+                        float* logits, int32_t* topk, float* scores, cudaStream_t st) {
+  GraphArgsAasist a = h->ga;
+  const aasist_config& c = h->cfg;
+  a.NT = NT;
+  a.nS = pooled_count(kSpecNodes, c.pool_ratios[0], 1);
+  a.nT = pooled_count(NT, c.pool_ratios[1], 1);
+  a.nS2 = pooled_count(a.nS, c.pool_ratios[2], 1);
+  a.nT2 = pooled_count(a.nT, c.pool_ratios[2], 1);
+  a.nmax = max(max(NT, kSpecNodes), a.nT + a.nS);
+  int dmax = max(max(a.C, a.g0), a.g1);
+  a.ld = dmax | 1;
+  a.e = e;
+  a.last_hidden = last_hidden;
+  a.logits = logits;
+  a.topk_idx = topk;
+  a.pool_scores = scores;
+  a.topk_total = a.nS + a.nT + 2 * (a.nS2 + a.nT2);
+  a.score_total = kSpecNodes + NT + 2 * (a.nS + a.nT);
+  size_t smem = sizeof(float) * (size_t)aasist_graph_smem_floats(a.nmax, a.ld, a.nS, a.nT, a.nS2, a.nT2);
+  if (smem > 227 * 1024) {
+    set_error("utterance too long for the on-chip graph stage: %d temporal nodes need %zu bytes "
+              "of shared memory (max 232448)", NT, smem);
+    return AASIST_E_INVALID;
+  }
+  AASIST_CUDA(cudaFuncSetAttribute(aasist_graph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+  {
+    LaunchSpan span(h, "aasist_graph", st);
+    aasist_graph_kernel<<<B, kGraphThreads, smem, st>>>(a);
+  }
+  AASIST_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// RawGAT-ST graph tail (RawNetGatSpoofST.py:338-356)
+// ---------------------------------------------------------------------------------------
+__host__ __device__ inline int rawgat_graph_smem_floats(int nmax, int ld) {
+  return scratch_floats(nmax) + (3 * nmax + 2 * 12 + 12 + 12) * ld + 64;
+}
+
+__global__ void __launch_bounds__(kGraphThreads)
+rawgat_graph_kernel(const GraphArgsRawGat a) {
+  extern __shared__ __align__(16) float smem[];
+  float* p = smem;
+  Scratch S;
+  carve_scratch(p, a.nmax, a.ld, S);
+  const int ld = a.ld;
+  float* B0 = bump(p, a.nmax * ld);
+  float* B1 = bump(p, a.nmax * ld);
+  S.AGG = bump(p, a.nmax * ld);
+  float* PT = bump(p, 12 * ld);   // proj_T output as 12 nodes x 32 features
+  float* PS = bump(p, 12 * ld);
+  float* G = bump(p, 12 * ld);
+  float* Q = bump(p, 12 * ld);
+  const int b = blockIdx.x;
+  const float* eT = a.eT + (size_t)b * 64 * kSpecNodes * a.NT;
+  const float* eS = a.eS + (size_t)b * 64 * kSpecNodes * a.NT;
+  int32_t* gi = a.topk_idx ? a.topk_idx + (size_t)b * a.topk_total : nullptr;
+  float* gw = a.pool_scores ? a.pool_scores + (size_t)b * a.score_total : nullptr;
+  const int D1 = a.gatT.Do;  // 32
+
+  // "T" branch: max over time -> 23 nodes (:338-341)
+  nodes_max_over_time(eT, 64, a.NT, nullptr, B0, ld);
+  gat_layer(B0, kSpecNodes, ld, a.gatT, B1, S);
+  graph_pool(B1, kSpecNodes, ld, a.poolT, a.nT, B0, gi, gw, S);
+  if (gi) gi += a.nT;
+  if (gw) gw += kSpecNodes;
+  // proj_T: Linear(nT,12) over the node axis of pool_T^T -> out_T (D1,12); kept as PT[m][d]
+  for (int t = threadIdx.x; t < 12 * D1; t += kGraphThreads) {
+    int m = t / D1, d = t % D1;
+    float s = 0.f;
+    for (int n = 0; n < a.nT; ++n) s = fmaf(__ldg(a.projTW + m * a.nT + n), B0[n * ld + d], s);
+    PT[m * ld + d] = s + __ldg(a.projTB + m);
+  }
+  __syncthreads();
+  // "S" branch: max over freq -> NT nodes (:343-347)
+  nodes_max_over_freq(eS, 64, a.NT, B0, ld);
+  gat_layer(B0, a.NT, ld, a.gatS, B1, S);
+  graph_pool(B1, a.NT, ld, a.poolS, a.nS, B0, gi, gw, S);
+  if (gi) gi += a.nS;
+  if (gw) gw += a.NT;
+  for (int t = threadIdx.x; t < 12 * D1; t += kGraphThreads) {
+    int m = t / D1, d = t % D1;
+    float s = 0.f;
+    for (int n = 0; n < a.nS; ++n) s = fmaf(__ldg(a.projSW + m * a.nS + n), B0[n * ld + d], s);
+    PS[m * ld + d] = s + __ldg(a.projSB + m);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < 12 * D1; t += kGraphThreads) {           // :349
+    int m = t / D1, d = t % D1;
+    G[m * ld + d] = PT[m * ld + d] * PS[m * ld + d];
+  }
+  __syncthreads();
+  gat_layer(G, 12, ld, a.gatST, Q, S);                                   // :351
+  graph_pool(Q, 12, ld, a.poolST, a.nST, B0, gi, gw, S);                 // :352
+  // proj_ST Linear(16,1) per node, then out_layer Linear(nST,2)         // :353-354
+  float* pr = S.wts;
+  for (int n = threadIdx.x; n < a.nST; n += kGraphThreads) {
+    float s = 0.f;
+    for (int d = 0; d < a.gatST.Do; ++d) s = fmaf(__ldg(a.projSTW + d), B0[n * ld + d], s);
+    s += a.projSTB;
+    pr[n] = s;
+    a.last_hidden[(size_t)b * a.nST + n] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    float s = 0.f;
+    for (int n = 0; n < a.nST; ++n) s = fmaf(__ldg(a.outW + threadIdx.x * a.nST + n), pr[n], s);
+    a.logits[(size_t)b * 2 + threadIdx.x] = s + __ldg(a.outB + threadIdx.x);
+  }
+}
+
+int launch_graph_rawgat(aasist_handle* h, const float* eT, const float* eS, int B, int NT,
+                        float* last_hidden, float* logits, int32_t* topk, float* scores,
+                        cudaStream_t st) {
+  GraphArgsRawGat a = h->gr;
+  a.NT = NT;
+  a.nT = pooled_count(kSpecNodes, 0.64, 2);
+  a.nS = pooled_count(NT, 0.81, 2);
+  a.nST = pooled_count(12, 0.64, 2);
+  if (a.nT != 14 || a.nS != 23 || a.nST != 7) {
+    set_error("RawGAT-ST is hard-wired to 64600-sample inputs (Linear(14,12)/Linear(23,12), "
+              "RawNetGatSpoofST.py:319-320); got %d temporal nodes", NT);
+    return AASIST_E_INVALID;
+  }
+  a.nmax = max(NT, kSpecNodes);
+  a.ld = 65;
+  a.eT = eT;
+  a.eS = eS;
+  a.last_hidden = last_hidden;
+  a.logits = logits;
+  a.topk_idx = topk;
+  a.pool_scores = scores;
+  a.topk_total = a.nT + a.nS + a.nST;
+  a.score_total = kSpecNodes + NT + 12;
+  size_t smem = sizeof(float) * (size_t)rawgat_graph_smem_floats(a.nmax, a.ld);
+  AASIST_CUDA(cudaFuncSetAttribute(rawgat_graph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+  {
+    LaunchSpan span(h, "rawgat_graph", st);
+    rawgat_graph_kernel<<<B, kGraphThreads, smem, st>>>(a);
+  }
+  AASIST_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace aasist

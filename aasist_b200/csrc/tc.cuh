@@ -1,0 +1,15 @@
+// Tensor-core (tcgen05, fp16 hi/lo split x3) path: entry points used by api.cu.
+#pragma once
+#include "common.cuh"
+
+namespace aasist {
+int tc_finalize(aasist_handle* h);
+void tc_destroy(aasist_handle* h);
+size_t tc_workspace_bytes(const aasist_handle* h, int B, int L);
+// x (B,L) -> enc_out[e] (B,C,23,NT) fp32 NCHW for every encoder of the model
+int tc_encode(aasist_handle* h, const float* x, int B, int L, float** enc_out, void* ws, cudaStream_t st);
+int tc_frontend_to_f32(aasist_handle* h, const float* x, int B, int L, float* out, void* ws,
+                       int64_t ws_bytes, cudaStream_t st);
+int tc_block_f32io(aasist_handle* h, int enc, int index, const float* in, int B, int W, float* out,
+                   void* ws, int64_t ws_bytes, cudaStream_t st);
+}  // namespace aasist

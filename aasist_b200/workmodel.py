@@ -1,0 +1,46 @@
+"""Algorithmic work of the hot path (2 x MAC of the reference's fp32 ops, unpadded, counted once
+whatever the kernel executes) -- used for roofline fractions."""
+from __future__ import annotations
+
+from .configs import CONFIGS
+
+
+def stage_macs(name: str, length: int = 64600):
+    """MACs per utterance by stage: {'sinc', 'enc{i}.conv1', 'enc{i}.conv2', 'enc{i}.ds', 'graph'}."""
+    cfg = CONFIGS[name]
+    f = cfg["filts"]
+    taps = cfg["first_conv"] + 1 if cfg["first_conv"] % 2 == 0 else cfg["first_conv"]
+    t = length - taps + 1
+    out = {"sinc": f[0] * taps * t}
+    w = t // 3
+    chans = [f[1], f[2], f[3], f[4], f[4], f[4]]
+    n_enc = 2 if name == "RawGAT-ST" else 1
+    for i, (ci, co) in enumerate(chans):
+        out[f"enc{i}.conv1"] = n_enc * co * ci * 6 * 24 * w
+        out[f"enc{i}.conv2"] = n_enc * co * co * 6 * 23 * w
+        out[f"enc{i}.ds"] = n_enc * (co * ci * 3 * 23 * w if ci != co else 0)
+        w //= 3
+    out["graph"] = {"AASIST": 11.6e6, "AASIST-L": 2.55e6, "RawGAT-ST": 3.25e6}[name]
+    return out
+
+
+def kernel_flops(name: str, kernel: str, batch: int, length: int = 64600) -> float:
+    """Algorithmic FLOPs per forward of all launches reported under `kernel`."""
+    m = stage_macs(name, length)
+    if kernel.startswith("sinc_frontend"):
+        macs = m["sinc"]
+    elif kernel.startswith("conv1") and "[1->C]" in kernel:
+        macs = m["enc0.conv1"]
+    elif kernel.startswith("conv1"):
+        macs = sum(m[f"enc{i}.conv1"] for i in range(1, 6))
+    elif kernel.startswith("conv2"):
+        macs = sum(m[f"enc{i}.conv2"] + m[f"enc{i}.ds"] for i in range(6))
+    elif kernel.startswith("block0"):
+        macs = m["enc0.conv1"] + m["enc0.conv2"] + m["enc0.ds"]
+    elif kernel.startswith("block"):
+        macs = sum(m[f"enc{i}.conv1"] + m[f"enc{i}.conv2"] + m[f"enc{i}.ds"] for i in range(1, 6))
+    elif "graph" in kernel:
+        macs = m["graph"]
+    else:
+        macs = 0.0
+    return 2.0 * macs * batch

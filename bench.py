@@ -1,0 +1,308 @@
+"""bench.py -- AASIST batched utterance scoring on B200: utterances/sec, roofline, CPU baseline.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun)
+    python bench.py --impl reference --steps K --warmup W    (CPU oracle port on the host cores)
+
+A "step" is one pass of the hot path (Model.forward) over one batch of synthetic 4 s / 16 kHz
+waveforms per GPU.  Workload at N=1 = BASELINE.json configs[1]: AASIST (config/AASIST.conf,
+models/weights/AASIST.pth), batch 512, L=64600.  N>1: every rank scores its own 512-utterance
+shard and the bona-fide scores are all-gathered over NCCL each step (weak scaling).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+L_SAMPLES = 64600
+# algorithmic FLOPs per utterance (2 x MAC of the reference fp32 ops, SURVEY 8(d) / BASELINE.md 4)
+FLOPS_PER_UTT = {"AASIST": 19.1241e9, "AASIST-L": 13.2063e9, "RawGAT-ST": 37.044e9}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--model", default="AASIST", choices=["AASIST", "AASIST-L", "RawGAT-ST"])
+    ap.add_argument("--batch", type=int, default=512)
+    ap.add_argument("--precision", default=None, help="fp32 | f16x3 (default: package default)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (the reference is pure Python/torch, nothing compiles into oracle/_ref)
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle_throughput(model_name: str, n_utt: int, repeats: int, warmup: int = 1):
+    import torch
+    from oracle import aasist_oracle as O
+    import aasist_b200
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    sd = torch.load(aasist_b200.weights_path(model_name), map_location="cpu")
+    cfg = O.CONFIGS[model_name]
+    x = O.white_noise(n_utt, L_SAMPLES, 1234)
+    bank = O.sinc_filterbank(cfg["filts"][0], cfg["first_conv"])
+    times = []
+    for i in range(warmup + repeats):
+        t0 = time.perf_counter()
+        O.forward(model_name, sd, cfg, x, None, bank)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return n_utt / min(times), n_utt * repeats / sum(times), cores, times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # bounded sample: size each step so that the whole run stays within a few minutes
+    probe_rate, _, cores, _ = cpu_oracle_throughput(args.model, 4, 1, warmup=1)
+    budget_s = 150.0
+    n_steps = args.steps + args.warmup
+    per_step = int(max(2, min(24, budget_s * probe_rate / max(1, n_steps))))
+    best, mean, cores, times = cpu_oracle_throughput(args.model, per_step, args.steps, warmup=args.warmup)
+    ms = 1e3 * sum(times) / len(times)
+    line = {
+        "impl": "reference", "metric": "AASIST utterances/sec (4 s, 64600 samples)", "value": mean,
+        "unit": "utt/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.model} (config/{args.model}.conf + shipped weights) eval forward, "
+                               f"L={L_SAMPLES}; CPU sample of {per_step} utterances per step "
+                               f"(the GPU arm's step is {args.batch} utterances per GPU)",
+                   "model_name": args.model, "batch_per_step": per_step, "samples": L_SAMPLES},
+        "cpu_baseline": {"value": mean, "unit": "utt/s", "cores": cores, "kind": "port",
+                         "sample": f"{per_step} utterances x {args.steps} steps, torch {cores} threads, "
+                                   "oracle/aasist_oracle.py (functional restatement of the reference forward)"},
+        "e2e": {"value": mean, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.idx)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        try:
+            for line in open(self.path):
+                f = [t.strip() for t in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                    power.append(float(f[3]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                   f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=max(power))
+        return out
+
+
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+
+    import aasist_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("for --gpus N>1 launch with: python -m torch.distributed.run --nnodes=1 "
+                         "--nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    name, B = args.model, args.batch
+    cls = aasist_b200.RawGATSTModel if name == "RawGAT-ST" else aasist_b200.Model
+    model = cls(aasist_b200.CONFIGS[name], precision=args.precision)
+    model.load_state_dict(torch.load(aasist_b200.weights_path(name), map_location="cpu"), strict=True)
+    model = model.to(dev).eval()
+    precision = model.precision
+
+    # synthetic 4 s waveforms, already resident in HBM for the device-timed region.
+    # 512 x 64600 fp32 = 132 MB per GPU > the 126 MB L2, and every intermediate is far larger,
+    # so no timed iteration can be served from L2.
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x = 0.05 * torch.randn(B, L_SAMPLES, device=dev, generator=g)
+    gathered = torch.empty(world * B, device=dev) if world > 1 else None
+
+    def step():
+        _, out = model(x)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out[:, 1].contiguous())
+        return out
+
+    with torch.no_grad():
+        for _ in range(max(3, args.warmup)):
+            out = step()
+        torch.cuda.synchronize()
+        model.profile(True)
+        model.profile_report(reset=True)
+        launches0 = model.launch_count()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(args.steps):
+            out = step()
+        ev1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        elapsed_ms = ev0.elapsed_time(ev1)
+        clocks = sampler.stop() if rank == 0 else None
+        launches = model.launch_count() - launches0
+        prof = model.profile_report(reset=True)
+        model.profile(False)
+        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+
+        # end to end through the public host-buffer call: pinned host input -> H2D -> forward ->
+        # D2H of (last_hidden, logits), every step (reference main.py:372-377 does the same per batch)
+        e2e = None
+        if not args.no_e2e:
+            xh = x.cpu().pin_memory()
+            model.score_host(xh)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n_e2e = max(2, min(args.steps, 5))
+            e0.record()
+            for _ in range(n_e2e):
+                lh_h, out_h = model.score_host(xh)
+                if world > 1:
+                    dist.all_gather_into_tensor(gathered, out_h[:, 1].to(dev, non_blocking=True))
+            e1.record()
+            torch.cuda.synchronize()
+            te = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            e2e = {"value": world * B * n_e2e / (float(te.item()) * 1e-3), "unit": "utt/s",
+                   "h2d_bytes_per_step": B * L_SAMPLES * 4, "d2h_bytes_per_step": B * (model.hidden_dim + 2) * 4,
+                   "steps": n_e2e}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = world * B * args.steps / (elapsed_ms * 1e-3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    # roofline of the dominant kernel (largest share of the timed region, CUDA events per launch)
+    prof.sort(key=lambda r: -r["ms"])
+    total_kernel_ms = sum(r["ms"] for r in prof) or 1.0
+    top = prof[0] if prof else None
+    roofline = None
+    if top is not None:
+        from aasist_b200 import workmodel
+        flops = workmodel.kernel_flops(name, top["kernel"], B, L_SAMPLES)      # algorithmic FLOPs / step
+        peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PF sustained (B200_PROFILING.md)"
+        ach = flops * args.steps / (top["ms"] * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": top["kernel"], "achieved": ach, "peak": peak_tf,
+                    "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                    "peak_source": peak_src, "share_of_step": top["ms"] / total_kernel_ms,
+                    "flops_per_launch_group": flops,
+                    "note": "achieved = algorithmic (2xMAC, fp32-reference) FLOPs of this kernel's launches "
+                            "per step / their CUDA-event time; fp32 path runs on CUDA cores, f16x3 executes 3 MMAs per MAC"}
+    line = {
+        "metric": "AASIST utterances/sec (4 s, 64600 samples)", "value": value, "unit": "utt/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32" if precision == "fp32" else "f16x3(split)+f32acc",
+        "data": "synthetic",
+        "config": {"workload": f"{name} (config/{name}.conf, shipped {name}.pth) eval scoring forward, "
+                               f"batch {B} per GPU, L={L_SAMPLES}",
+                   "model_name": name, "batch_per_gpu": B, "global_batch": B * world, "samples": L_SAMPLES,
+                   "precision": precision, "parallelism": f"utterance-sharded dp{world}, one NCCL all-gather of scores per step",
+                   "l2_policy": "inputs (132 MB/GPU) and every intermediate exceed the 126 MB L2"},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": roofline,
+        "kernels": [{"kernel": r["kernel"], "launches": r["launches"], "ms_per_step": r["ms"] / args.steps,
+                     "share": r["ms"] / total_kernel_ms} for r in prof],
+        "algorithmic_tflops": value * FLOPS_PER_UTT[name] / 1e12,
+    }
+    if not args.no_cpu_baseline and world >= 1:
+        n_cpu = 8
+        best, mean, cores, times = cpu_oracle_throughput(name, n_cpu, 2, warmup=1)
+        line["cpu_baseline"] = {"value": best, "unit": "utt/s", "cores": cores, "kind": "port",
+                                "sample": f"{n_cpu} utterances, best of 2 after 1 warm-up, torch CPU fp32, "
+                                          f"{cores} threads (oracle/aasist_oracle.py)"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_native(a)

@@ -1,0 +1,155 @@
+/*
+ * aasist_b200.h -- C ABI of libaasist_b200.so: the B200 (sm_100a) implementation of the
+ * AASIST / RawGAT-ST batched utterance-scoring forward pass.
+ *
+ * This is the drop-in boundary for the reference's model plug-in interface
+ * (reference main.py:251-259 `get_model`, README.md:69-77): everything the reference does
+ * between `model(batch_x)` (main.py:376) and the returned `(last_hidden, output)` tuple
+ * (models/AASIST.py:806-921, models/RawNetGatSpoofST.py:324-356) happens behind these
+ * entry points.  Plain C types only: raw pointers, sizes, an opaque handle and a
+ * `cudaStream_t` passed as `void*`.  No torch types, no exceptions.  Every function returns
+ * 0 on success and a negative `AASIST_E_*` code on failure; `aasist_last_error()` gives the
+ * message of the calling thread's most recent failure.  A handle is bound to the CUDA
+ * device that was current at `aasist_create` and is not thread-safe.
+ *
+ * There is NO CPU fallback: every compute entry point fails with AASIST_E_CUDA when no
+ * CUDA device is usable.
+ */
+#ifndef AASIST_B200_H_
+#define AASIST_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AASIST_B200_ABI_VERSION 1
+
+enum {
+  AASIST_OK = 0,
+  AASIST_E_INVALID = -1,   /* bad argument / shape (reference: RuntimeError / ValueError)   */
+  AASIST_E_STATE = -2,     /* call order violated (e.g. forward before finalize)            */
+  AASIST_E_PARAM = -3,     /* unknown / missing / mis-sized parameter (strict state_dict)   */
+  AASIST_E_CUDA = -4,      /* CUDA runtime/driver error, or no device                        */
+  AASIST_E_WORKSPACE = -5  /* workspace too small                                           */
+};
+
+/* model kinds: which reference `Model.forward` is reproduced */
+enum {
+  AASIST_KIND_AASIST = 0,   /* models/AASIST.py:728-921 with the (2,3) Residual_block encoder
+                               (models/RawNetGatSpoofST.py:225-278) the shipped weights fit   */
+  AASIST_KIND_RAWGAT_ST = 1 /* models/RawNetGatSpoofST.py:281-356                            */
+};
+
+/* arithmetic of the sinc / encoder convolutions (graph stages are always fp32) */
+enum {
+  AASIST_PREC_FP32 = 0,   /* fp32 FFMA on CUDA cores                                         */
+  AASIST_PREC_F16X3 = 1   /* tcgen05 tensor cores: fp16 hi/lo operand split, 3 products,
+                             fp32 accumulation in TMEM (logits within ~1e-5 of fp32)         */
+};
+
+/* Mirrors the reference's `model_config` dict (config/AASIST.conf:13-21) that
+ * `Model.__init__(d_args)` reads (models/AASIST.py:729-804). */
+typedef struct aasist_config {
+  int32_t kind;              /* AASIST_KIND_*                                                */
+  int32_t precision;         /* AASIST_PREC_*                                                */
+  int32_t first_conv;        /* d_args["first_conv"] (128 -> 129 taps, AASIST.py:449-450)    */
+  int32_t n_filters;         /* d_args["filts"][0]  (70; must give 23 pooled bands)          */
+  int32_t enc_channels[6][2];/* (in,out) of the six residual blocks: filts[1],[2],[3],[4]x3  */
+  int32_t gat_dims[2];       /* d_args["gat_dims"]            (AASIST kind only)             */
+  double pool_ratios[4];     /* d_args["pool_ratios"]         (AASIST kind only)             */
+  double temperatures[4];    /* d_args["temperatures"]        (AASIST kind only)             */
+  int32_t sample_rate;       /* 16000 (CONV.__init__ default, AASIST.py:430)                 */
+  int32_t reserved[7];
+} aasist_config;
+
+typedef struct aasist_handle aasist_handle;
+
+/* ---- life cycle ------------------------------------------------------------------------ */
+int aasist_abi_version(void);
+const char* aasist_last_error(void);
+
+/* Replaces `Model(d_args)` (reference main.py:255, models/AASIST.py:729). */
+int aasist_create(const aasist_config* cfg, aasist_handle** out);
+int aasist_destroy(aasist_handle* h);
+
+/* Replaces `model.load_state_dict(...)` (reference main.py:104-105), one tensor per call.
+ * `name` is the reference state_dict key (e.g. "encoder.0.0.conv1.weight"); `data` may be a
+ * host or a device pointer to `numel` fp32 values; the handle keeps its own copy.
+ * `*.num_batches_tracked` keys are accepted and ignored. */
+int aasist_set_param(aasist_handle* h, const char* name, const float* data, int64_t numel);
+/* Number of state_dict tensors the configuration expects / their names (for strict loading). */
+int aasist_num_params(const aasist_handle* h);
+const char* aasist_param_name(const aasist_handle* h, int index, int64_t* numel);
+/* Checks that every expected tensor was set, folds the eval-mode batch norms into the
+ * adjacent weights, repacks for the kernels and builds the sinc filter bank ON DEVICE
+ * (models/AASIST.py:460-482). */
+int aasist_finalize(aasist_handle* h);
+
+/* ---- the hot path ---------------------------------------------------------------------- */
+/* Bytes of scratch `aasist_forward` needs for a batch of B utterances of L samples. */
+int64_t aasist_workspace_bytes(const aasist_handle* h, int32_t B, int32_t L);
+
+/* Width of `last_hidden`: 5*gat_dims[1] (AASIST.py:909-910) or 7 (RawNetGatSpoofST.py:353). */
+int aasist_hidden_dim(const aasist_handle* h);
+/* Total number of top-k indices written per utterance for length L (all GraphPools, in the
+ * order pool_S, pool_T, pool_hS1, pool_hT1, pool_hS2, pool_hT2  /  pool_T, pool_S, pool_ST),
+ * and per-pool (n_nodes_in, k) pairs written to `nk` (2*n_pools ints) when not NULL. */
+int aasist_topk_layout(const aasist_handle* h, int32_t L, int32_t* n_pools, int32_t* nk);
+
+/* Replaces `Model.forward(x)` in eval mode (models/AASIST.py:806-921; Freq_aug=False,
+ * speaker_embedding=None).  All pointers are DEVICE pointers:
+ *   x            (B, L) fp32 waveforms, row-major
+ *   last_hidden  (B, hidden_dim) fp32 out
+ *   logits       (B, 2) fp32 out          -- `output`; the score is logits[:,1] (main.py:377)
+ *   topk_idx     (B, topk_total) int32 out, or NULL -- GraphPool indices in descending score
+ *                order (AASIST.py:316); exact ties are broken towards the lower node index
+ *   pool_scores  (B, sum of n_nodes_in) fp32 out, or NULL -- pre-sigmoid GraphPool weights
+ *   workspace    >= aasist_workspace_bytes(h,B,L) bytes, 256-byte aligned
+ *   stream       cudaStream_t (NULL = legacy default stream)
+ * Asynchronous with respect to the host. */
+int aasist_forward(aasist_handle* h, const float* x, int32_t B, int32_t L,
+                   float* last_hidden, float* logits, int32_t* topk_idx, float* pool_scores,
+                   void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Same call with HOST buffers: pinned staging + H2D of x, forward, D2H of logits and
+ * last_hidden (either may be NULL), stream-synchronised before return.  This is what
+ * reference main.py:372-377 does per batch (`.to(device)` ... `.cpu()`). */
+int aasist_forward_host(aasist_handle* h, const float* x_host, int32_t B, int32_t L,
+                        float* last_hidden_host, float* logits_host, void* stream);
+
+/* ---- per-stage entry points (parity tests; same kernels as aasist_forward) -------------- */
+/* Device copy of the sinc filter bank, (n_filters, taps) fp32, into `bank_dev`. */
+int aasist_get_filterbank(aasist_handle* h, float* bank_dev, int32_t* n_filters, int32_t* taps);
+/* Sinc conv + |.| + 3x3 max-pool + first_bn + SELU (AASIST.py:823-831):
+ * x (B,L) -> out (B,23,floor((L-taps+1)/3)) fp32 NCHW (one channel). */
+int aasist_frontend(aasist_handle* h, const float* x, int32_t B, int32_t L, float* out,
+                    void* workspace, int64_t workspace_bytes, void* stream);
+/* Residual block `index` (0..5) of encoder `enc` (0; RawGAT-ST: 0 = encoder_T, 1 = encoder_S)
+ * (RawNetGatSpoofST.py:258-278): in (B,Cin,23,W) -> out (B,Cout,23,floor(W/3)), fp32 NCHW. */
+int aasist_encoder_block(aasist_handle* h, int32_t enc, int32_t index, const float* in, int32_t B,
+                         int32_t W, float* out, void* workspace, int64_t workspace_bytes,
+                         void* stream);
+/* Everything after the encoder (AASIST.py:841-921 / RawNetGatSpoofST.py:338-356):
+ * e (B,C,23,NT) fp32 NCHW (RawGAT-ST: e = encoder_T output, e2 = encoder_S output). */
+int aasist_graph(aasist_handle* h, const float* e, const float* e2, int32_t B, int32_t NT,
+                 float* last_hidden, float* logits, int32_t* topk_idx, float* pool_scores,
+                 void* stream);
+
+/* Number of kernels this library has launched through the handle so far. */
+int64_t aasist_launch_count(const aasist_handle* h);
+
+/* Per-kernel device timing: while enabled, every launch made through the handle is bracketed
+ * by CUDA events recorded on the launching stream.  `aasist_profile_report` synchronises the
+ * device, folds the pending events into per-kernel totals and writes them as JSON
+ * (`[{"kernel": "...", "launches": n, "ms": total}, ...]`) into `buf`; `reset` != 0 clears the
+ * totals afterwards.  Returns the number of bytes written (excluding the NUL) or < 0. */
+int aasist_profile_enable(aasist_handle* h, int32_t enable);
+int aasist_profile_report(aasist_handle* h, char* buf, int64_t buf_bytes, int32_t reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AASIST_B200_H_ */

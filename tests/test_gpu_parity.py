@@ -1,0 +1,183 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the committed golden
+fixtures (generated from the reference itself).  fp32 CUDA-core path; the tensor-core path
+has its own file.  Tolerances are stated inline; GraphPool indices follow SURVEY 8(c)."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+import aasist_b200
+from oracle import aasist_oracle as O
+from tests.util import golden_input, load_golden, load_sd, pools_of
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 1e-4          # fp32 path: max-abs on logits / last_hidden (north_star: <= 1e-3)
+CASES = [("AASIST", "white"), ("AASIST", "speech"), ("AASIST", "speech16k"), ("AASIST", "speech96k"),
+         ("AASIST-L", "white"), ("AASIST-L", "speech"), ("AASIST-L", "speech16k"), ("AASIST-L", "speech96k"),
+         ("RawGAT-ST", "white"), ("RawGAT-ST", "speech")]
+
+
+def _g():
+    from tests import gpu_util
+    return gpu_util
+
+
+def test_filterbank_built_on_device_matches_reference_bank():
+    g = _g()
+    from aasist_b200 import _lib
+    m = g.native_model("AASIST")
+    bank = torch.empty(70, 129, device=g.DEV)
+    _lib.check(_lib.load().aasist_get_filterbank(m._handle, bank.data_ptr(), None, None))
+    gold, _ = load_golden("AASIST", "white")
+    err = np.abs(bank.cpu().numpy() - gold["bank"]).max()
+    # values <= 0.038; the device kernel reproduces the reference's fp32/fp64 dtype chain, the only
+    # freedom left is the last ulp of sin(): 1 ulp of 0.038 is 3.7e-9
+    assert err <= 8e-9, err
+
+
+@pytest.mark.parametrize("name", ["AASIST", "AASIST-L"])
+def test_frontend_stage(name):
+    g = _g()
+    x = O.speech_like(2, 64600, 3)
+    taps = g.oracle_taps(name, x)
+    out = g.stage_frontend(g.native_model(name), x.to(g.DEV))
+    ref = taps["frontend"]
+    err = (out.cpu() - ref).abs().max().item()
+    assert err <= 2e-4 * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.parametrize("name", ["AASIST", "AASIST-L", "RawGAT-ST"])
+def test_encoder_blocks_stagewise(name):
+    g = _g()
+    x = O.speech_like(2, 64600, 4)
+    taps = g.oracle_taps(name, x)
+    m = g.native_model(name)
+    cfg = O.CONFIGS[name]
+    f = cfg["filts"]
+    chans = [f[1], f[2], f[3], f[4], f[4], f[4]]
+    for e, pre in enumerate(["encoder_T", "encoder_S"] if name == "RawGAT-ST" else ["encoder"]):
+        inp = taps["frontend"]
+        for i in range(6):
+            ref = taps[f"{pre}.{i}"]
+            out = g.stage_block(m, e, i, inp.to(g.DEV), chans[i][1])
+            err = (out.cpu() - ref).abs().max().item()
+            assert err <= 2e-5 * max(1.0, ref.abs().max().item()), (pre, i, err)
+            inp = ref
+
+
+@pytest.mark.parametrize("name,tag", [("AASIST", "speech"), ("AASIST", "white"), ("AASIST-L", "speech"),
+                                      ("AASIST", "speech96k"), ("AASIST-L", "speech16k")])
+def test_graph_stage_from_golden_encoder_output(name, tag):
+    g = _g()
+    gold, meta = load_golden(name, tag)
+    e = torch.from_numpy(gold["encoder.5.full"]).to(g.DEV)
+    lh, lg, pools = g.stage_graph(g.native_model(name), e, L=meta["L"])
+    assert np.abs(lg.cpu().numpy() - gold["output"]).max() <= LOGIT_TOL
+    assert np.abs(lh.cpu().numpy() - gold["last_hidden"]).max() <= LOGIT_TOL
+    rep = g.check_pools(pools, gold, pools_of(name))
+    for p, r in rep.items():
+        assert r["weights_err"] <= 5e-5, (p, r)
+        assert r["mismatch_outside_near_ties"] == 0, (p, r)
+    if tag == "speech":
+        assert sum(r["strict_mismatch"] for r in rep.values()) == 0, rep
+
+
+def test_graph_stage_rawgat_from_golden():
+    g = _g()
+    gold, meta = load_golden("RawGAT-ST", "speech")
+    eT = torch.from_numpy(gold["encoder_T.5.full"]).to(g.DEV)
+    eS = torch.from_numpy(gold["encoder_S.5.full"]).to(g.DEV)
+    lh, lg, pools = g.stage_graph(g.native_model("RawGAT-ST"), eT, eS)
+    assert np.abs(lg.cpu().numpy() - gold["output"]).max() <= LOGIT_TOL
+    assert np.abs(lh.cpu().numpy() - gold["last_hidden"]).max() <= LOGIT_TOL
+    rep = g.check_pools(pools, gold, pools_of("RawGAT-ST"))
+    for p, r in rep.items():
+        assert r["weights_err"] <= 5e-5 and r["mismatch_outside_near_ties"] == 0, (p, r)
+
+
+@pytest.mark.parametrize("name,tag", CASES)
+def test_full_forward_against_golden(name, tag):
+    g = _g()
+    gold, meta = load_golden(name, tag)
+    x = golden_input(meta).to(g.DEV)
+    m = g.native_model(name)
+    m.record_topk = True
+    try:
+        last_hidden, output = m(x)
+        torch.cuda.synchronize()
+        pools = g.split_pools(m.last_topk, m.last_pool_weights, m.topk_layout(meta["L"]))
+    finally:
+        m.record_topk = False
+    assert output.shape == (meta["n"], 2) and last_hidden.shape[1] == gold["last_hidden"].shape[1]
+    assert np.abs(output.cpu().numpy() - gold["output"]).max() <= LOGIT_TOL
+    assert np.abs(last_hidden.cpu().numpy() - gold["last_hidden"]).max() <= LOGIT_TOL
+    rep = g.check_pools(pools, gold, pools_of(name))
+    for p, r in rep.items():
+        assert r["weights_err"] <= 1e-4, (p, r)
+        assert r["mismatch_outside_near_ties"] == 0, (p, r)
+    print(json.dumps({"case": f"{name}/{tag}", "pools": rep}))
+
+
+def test_input_forms_batch_invariance_and_determinism():
+    g = _g()
+    m = g.native_model("AASIST")
+    x = O.speech_like(5, 64600, 21).to(g.DEV)
+    lh, out = m(x)
+    lh3, out3 = m(x.unsqueeze(1))                       # (B,1,L) accepted (AASIST.py:816-817)
+    assert torch.equal(out, out3) and torch.equal(lh, lh3)
+    out_again = m(x)[1]
+    assert torch.equal(out, out_again)                  # deterministic
+    single = torch.cat([m(x[i:i + 1])[1] for i in range(5)])
+    assert torch.equal(out, single)                     # utterances are independent (shard invariance)
+    xs = torch.empty(5, 2 * 64600, device=g.DEV)[:, ::2]
+    xs.copy_(x)
+    assert torch.equal(m(xs)[1], out)                   # non-contiguous input
+
+
+def test_error_behaviour_matches_reference_contract():
+    g = _g()
+    m = g.native_model("AASIST")
+    with pytest.raises(RuntimeError):                   # reference: RuntimeError for L < 2315
+        m(torch.zeros(1, 2000, device=g.DEV))
+    m(torch.zeros(1, 2315, device=g.DEV))               # shortest valid length
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(2, 64600))                        # CPU tensor: no fallback
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 64600, device=g.DEV), Freq_aug=True)
+    r = g.native_model("RawGAT-ST")
+    with pytest.raises(RuntimeError):                   # hard-wired to 64600 (Linear(14,12)/(23,12))
+        r(torch.zeros(1, 32000, device=g.DEV))
+
+
+def test_forward_host_equals_device_forward():
+    g = _g()
+    m = g.native_model("AASIST-L")
+    x = O.speech_like(3, 64600, 22)
+    lh_d, out_d = m(x.to(g.DEV))
+    lh_h, out_h = m.score_host(x.pin_memory())
+    assert torch.equal(out_d.cpu(), out_h) and torch.equal(lh_d.cpu(), lh_h)
+    lh_p, out_p = m.score_host(x)                       # pageable host memory
+    assert torch.equal(out_p, out_h)
+
+
+def test_zero_and_constant_inputs():
+    g = _g()
+    for name in ("AASIST", "AASIST-L"):
+        x = torch.zeros(2, 64600)
+        x[1] = 0.25
+        taps = g.oracle_taps(name, x)
+        out = g.native_model(name)(x.to(g.DEV))[1]
+        assert (out.cpu() - taps["output"]).abs().max().item() <= LOGIT_TOL
+
+
+def test_scoring_loop_matches_oracle_scores():
+    g = _g()
+    from aasist_b200.scoring import score_utterances
+    m = g.native_model("AASIST-L")
+    x = O.speech_like(7, 64600, 23)
+    scores = score_utterances(m, x, 7, batch_size=3)
+    ref = g.oracle_taps("AASIST-L", x)["output"][:, 1]
+    assert scores.shape == (7,)
+    assert (scores.cpu() - ref).abs().max().item() <= LOGIT_TOL
