@@ -1,10 +1,781 @@
-// placeholder until the tcgen05 path lands
+// Residual_block encoder on the 5th-generation tensor cores (reference
+// models/RawNetGatSpoofST.py:225-278), fp16 hi/lo split operands, 3 products, fp32 accumulation
+// in tensor memory:   a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo   (a = a_hi + a_lo, fp16 each).
+//
+// Activation layout in HBM ("phase-split pairs"):  act[b][h][phi][j][2*Cp] fp16, where the
+// time position is w = 3*j + phi and the innermost vector is [hi(Cp) | lo(Cp)].  Splitting the
+// time axis by w mod 3 makes the MaxPool2d((1,3)) lane-local: a CTA tile is 128 pooled
+// columns j of one (utterance, row); the three pool phases s are three accumulators in TMEM and
+// the epilogue takes max_s in registers.  A conv tap (dh,dw) for phase s reads input phase
+// (s+dw-1) mod 3 shifted by floor((s+dw-1)/3) rows -- expressed as a +-128-byte offset of the
+// UMMA shared-memory descriptor into ONE TMA-loaded tile of 130 rows, so each input tile is
+// loaded once and feeds three accumulators.  Zero padding (conv pad (1,1)/(0,1)) is TMA
+// out-of-bounds fill; positions >= W are kept zero in memory by every producer.
+//
+// Kernel structure (persistent, 1 CTA/SM, 192 threads): warp 0 = TMA producer, warp 1 = TMEM
+// allocator + single-thread tcgen05.mma issuer, warps 2-5 = epilogue (tcgen05.ld -> bias /
+// SELU / residual / max-pool -> hi/lo split -> 128-byte vector stores).  smem ring of input
+// tiles (full/empty mbarriers), double-buffered accumulators (tmem_full/tmem_empty mbarriers).
+#include <algorithm>
+
+#include "ptx.cuh"
 #include "tc.cuh"
+
 namespace aasist {
-int tc_finalize(aasist_handle*) { set_error("f16x3 tensor-core path not built"); return AASIST_E_STATE; }
-void tc_destroy(aasist_handle*) {}
-size_t tc_workspace_bytes(const aasist_handle*, int, int) { return 0; }
-int tc_encode(aasist_handle*, const float*, int, int, float**, void*, cudaStream_t) { set_error("f16x3 path not built"); return AASIST_E_STATE; }
-int tc_frontend_to_f32(aasist_handle*, const float*, int, int, float*, void*, int64_t, cudaStream_t) { set_error("f16x3 path not built"); return AASIST_E_STATE; }
-int tc_block_f32io(aasist_handle*, int, int, const float*, int, int, float*, void*, int64_t, cudaStream_t) { set_error("f16x3 path not built"); return AASIST_E_STATE; }
+
+using namespace ptx;
+
+constexpr int kTileJ = 128;                 // pooled columns per CTA tile (UMMA M)
+constexpr int kBoxRows = kTileJ + 2;        // rows j0-1 .. j0+128
+constexpr int kSlabBytes = 17 * 1024;       // 130 rows x 128 B, rounded up to the 1024-B swizzle atom
+constexpr int kTcThreads = 192;
+constexpr int kMaxSlots = 8;
+constexpr int kChunkTc = 128;               // utterances per encoder pass (bounds scratch)
+
+enum { TC_CONV1 = 0, TC_CONV2_ID = 1, TC_CONV2_DS = 2, TC_CONV2_Z = 3 };
+
+struct ConvTcParams {
+  int B, H_out, J, n_jt, W_in, Co, Wo, Jn;
+  int n_slots;
+  const float* bias;       // [COP]
+  __half* out;             // CONV1: [B][24][3][J][2*COP]; CONV2: [B][23][3][Jn][2*COP]
+  float* out_f32;          // last block: (B,Co,23,Wo) fp32 NCHW (then `out` is unused)
+  const __half* idn;       // CONV2_ID: block input, [B][23][3][J][2*COP]
+  const float* z;          // CONV2_Z: block-0 input (B,23,W_in) fp32
+  const float* wd;         // CONV2_Z: conv_downsample weights [3][COP] fp32
+  const uint8_t* wimg;     // pre-swizzled weight image (shared-memory layout)
+  int wimg_bytes;
+};
+
+struct ConvTc {            // one convolution's packed device state
+  uint8_t* wimg = nullptr;
+  int wimg_bytes = 0;
+  float* bias = nullptr;
+};
+struct BlockTc {
+  int ci = 0, co = 0, cpi = 0, cop = 0;
+  bool downsample = false;
+  ConvTc c1, c2;
+  float* w1_f32 = nullptr;   // block 0 only: conv1 (bn2 folded) [6][32] fp32
+  float* wd_f32 = nullptr;   // block 0 only: conv_downsample [3][32] fp32
+};
+struct TcState {
+  BlockTc blocks[2][6];
+  int sm_count = 148;
+  void* encode_fn = nullptr;  // cuTensorMapEncodeTiled
+};
+
+__device__ __forceinline__ float selu_fast(float v) {
+  // negative branch through MUFU.EX2: |abs error| <= ~2.5e-7 (same order as the fp16-pair
+  // representation error of the stored activation)
+  return v > 0.f ? kSeluScale * v : (kSeluScale * kSeluAlpha) * (exp2f(v * 1.4426950408889634f) - 1.f);
 }
+__device__ __forceinline__ float clamp_h(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
+
+// store 32 fp32 channels as hi (64 B) and lo (64 B) fp16 vectors
+__device__ __forceinline__ void store_pair32(__half* hi_dst, __half* lo_dst, const float (&v)[32]) {
+  uint32_t hw[16], lw[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    __half h0, l0, h1, l1;
+    split_f16(clamp_h(v[2 * i]), h0, l0);
+    split_f16(clamp_h(v[2 * i + 1]), h1, l1);
+    hw[i] = pack_h2(h0, h1);
+    lw[i] = pack_h2(l0, l1);
+  }
+  uint4* hd = reinterpret_cast<uint4*>(hi_dst);
+  uint4* ld = reinterpret_cast<uint4*>(lo_dst);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    hd[i] = make_uint4(hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]);
+    ld[i] = make_uint4(lw[4 * i], lw[4 * i + 1], lw[4 * i + 2], lw[4 * i + 3]);
+  }
+}
+// v[i] += float(hi[i]) + float(lo[i]) for 32 channels
+__device__ __forceinline__ void add_pair32(const __half* hi_src, const __half* lo_src, float (&v)[32]) {
+  const uint4* hs = reinterpret_cast<const uint4*>(hi_src);
+  const uint4* ls = reinterpret_cast<const uint4*>(lo_src);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 a = __ldg(hs + i), b = __ldg(ls + i);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float2 fa = __half22float2(*reinterpret_cast<const __half2*>(&aw[k]));
+      float2 fb = __half22float2(*reinterpret_cast<const __half2*>(&bw[k]));
+      v[8 * i + 2 * k] += fa.x + fb.x;
+      v[8 * i + 2 * k + 1] += fa.y + fb.y;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// implicit-GEMM (2,3)/(1,3) convolution on tcgen05
+// ------------------------------------------------------------------------------------------
+template <int CPI, int COP, int MODE>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmS,
+               const ConvTcParams p) {
+  constexpr int SLABS = CPI / 32;                    // 128-byte-wide K slabs per input tile
+  constexpr int SLOT_BYTES = SLABS * kSlabBytes;
+  constexpr int KC = CPI / 16;                       // K chunks (UMMA_K = 16) per product
+  constexpr int TAP_BYTES = SLABS * COP * 128;       // weight image bytes per tap (main input)
+  constexpr int SIDE_TAP_BYTES = COP * 128;          // side input is 32 channels wide (1 slab)
+  constexpr int TMEM_COLS = (6 * COP <= 256) ? 256 : 512;
+  constexpr uint32_t IDESC = umma_idesc_f16(128, COP);
+  constexpr int N_MAIN = 6;
+  constexpr int N_SIDE = (MODE == TC_CONV2_DS) ? 3 : 0;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* s_w = smem;
+  uint8_t* s_ring = smem + p.wimg_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + (size_t)p.n_slots * SLOT_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kMaxSlots;
+  uint64_t* tfull = bars + 2 * kMaxSlots;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = p.B * p.H_out * p.n_jt;
+
+  // weights: global image -> shared (generic proxy), then make visible to the async proxy
+  for (int i = threadIdx.x; i < p.wimg_bytes / 16; i += kTcThreads)
+    reinterpret_cast<uint4*>(s_w)[i] = __ldg(reinterpret_cast<const uint4*>(p.wimg) + i);
+  fence_proxy_async_smem();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.n_slots; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);     // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+    prefetch_tensormap(&tmA);
+    if (N_SIDE) prefetch_tensormap(&tmS);
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_ptr);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int h = t % p.H_out, jt = (t / p.H_out) % p.n_jt, b = t / (p.H_out * p.n_jt);
+        const int j0 = jt * kTileJ - 1;
+        for (int it = 0; it < N_MAIN + N_SIDE; ++it) {
+          mbar_wait(&empty[slot], phase ^ 1);
+          uint8_t* dst = s_ring + (size_t)slot * SLOT_BYTES;
+          if (it < N_MAIN) {
+            const int dh = it / 3, phi = it % 3;
+            const int row = (MODE == TC_CONV1) ? h + dh - 1 : h + dh;   // TMA zero-fills row -1 / 23
+            mbar_arrive_expect_tx(&full[slot], SLABS * kBoxRows * 128);
+#pragma unroll
+            for (int sl = 0; sl < SLABS; ++sl)
+              tma_load_5d(dst + sl * kSlabBytes, &tmA, &full[slot], sl * 64, j0, phi, row, b);
+          } else {
+            const int phi = it - N_MAIN;
+            mbar_arrive_expect_tx(&full[slot], kBoxRows * 128);
+            tma_load_5d(dst, &tmS, &full[slot], 0, j0, phi, h, b);
+          }
+          if (++slot == p.n_slots) { slot = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ==================================
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t phase = 0;
+      int tcount = 0;
+      const uint32_t w_base = smem_u32(s_w);
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
+        const int buf = tcount & 1;
+        mbar_wait(&tempty[buf], ((tcount >> 1) & 1) ^ 1);
+        tc_fence_after_sync();
+        uint32_t started = 0;   // bit s: accumulator s already holds a partial sum
+        for (int it = 0; it < N_MAIN + N_SIDE; ++it) {
+          mbar_wait(&full[slot], phase);
+          tc_fence_after_sync();
+          const uint32_t a_slot = smem_u32(s_ring + (size_t)slot * SLOT_BYTES);
+          const bool side = it >= N_MAIN;
+          const int dh = side ? 0 : it / 3, phi = side ? it - N_MAIN : it % 3;
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            const int d = (phi - s + 3) % 3;              // input phase phi serves pool phase s via tap dw
+            const int dw = d == 0 ? 1 : (d == 1 ? 2 : 0);
+            const int pp = s + dw - 1;                    // input position offset in units of phase steps
+            const int shift = pp < 0 ? -1 : (pp > 2 ? 1 : 0);
+            const uint32_t a_row = a_slot + (uint32_t)(1 + shift) * 128;
+            const uint32_t d_tmem = tmem_base + (uint32_t)((buf * 3 + s) * COP);
+            if (!side) {
+              const uint32_t wt = w_base + (uint32_t)((dh * 3 + dw) * TAP_BYTES);
+#pragma unroll
+              for (int kc = 0; kc < KC; ++kc) {
+                const uint32_t a_hi = a_row + kc * 32;
+                const uint32_t a_lo = (SLABS == 1) ? a_row + 64 + kc * 32 : a_row + kSlabBytes + kc * 32;
+                const uint32_t w_hi = wt + kc * 32;
+                const uint32_t w_lo = (SLABS == 1) ? wt + 64 + kc * 32 : wt + COP * 128 + kc * 32;
+                umma_f16(d_tmem, umma_desc_sw128(a_hi), umma_desc_sw128(w_hi), IDESC, (started >> s) & 1);
+                started |= 1u << s;
+                umma_f16(d_tmem, umma_desc_sw128(a_lo), umma_desc_sw128(w_hi), IDESC, 1);
+                umma_f16(d_tmem, umma_desc_sw128(a_hi), umma_desc_sw128(w_lo), IDESC, 1);
+              }
+            } else {
+              const uint32_t wt = w_base + (uint32_t)(6 * TAP_BYTES + dw * SIDE_TAP_BYTES);
+#pragma unroll
+              for (int kc = 0; kc < 2; ++kc) {
+                const uint32_t a_hi = a_row + kc * 32, a_lo = a_row + 64 + kc * 32;
+                const uint32_t w_hi = wt + kc * 32, w_lo = wt + 64 + kc * 32;
+                umma_f16(d_tmem, umma_desc_sw128(a_hi), umma_desc_sw128(w_hi), IDESC, 1);
+                umma_f16(d_tmem, umma_desc_sw128(a_lo), umma_desc_sw128(w_hi), IDESC, 1);
+                umma_f16(d_tmem, umma_desc_sw128(a_hi), umma_desc_sw128(w_lo), IDESC, 1);
+              }
+            }
+          }
+          umma_commit(&empty[slot]);                      // slot reusable once these MMAs retire
+          if (++slot == p.n_slots) { slot = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[buf]);                         // accumulators of this tile complete
+      }
+    }
+  } else {
+    // =============================== epilogue (warps 2..5) ========================
+    const int quad = warp & 3;                            // TMEM lane quadrant this warp may access
+    const int r = quad * 32 + lane;                       // accumulator row == pooled column offset
+    int tcount = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
+      const int h = t % p.H_out, jt = (t / p.H_out) % p.n_jt, b = t / (p.H_out * p.n_jt);
+      const int buf = tcount & 1;
+      const int j = jt * kTileJ + r;
+      mbar_wait(&tfull[buf], (tcount >> 1) & 1);
+      tc_fence_after_sync();
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 3 * COP);
+      if (MODE == TC_CONV1) {
+        // out[b][h][s][j][:] = selu(acc + b1), zero beyond the valid width
+#pragma unroll 1
+        for (int s = 0; s < 3; ++s) {
+#pragma unroll
+          for (int q = 0; q < COP / 32; ++q) {
+            float v[32];
+            tmem_ld32(t_row + (uint32_t)(s * COP + q * 32), v);
+            const bool valid = 3 * j + s < p.W_in;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = valid ? selu_fast(v[i] + __ldg(p.bias + q * 32 + i)) : 0.f;
+            if (j < p.J) {
+              __half* o = p.out + ((((size_t)b * 24 + h) * 3 + s) * p.J + j) * (2 * COP);
+              store_pair32(o + q * 32, o + COP + q * 32, v);
+            }
+          }
+        }
+      } else {
+        float zq[5];
+        if (MODE == TC_CONV2_Z) {
+          const float* zr = p.z + ((size_t)b * 23 + h) * p.W_in;
+#pragma unroll
+          for (int i = 0; i < 5; ++i) {
+            int w = 3 * j - 1 + i;
+            zq[i] = (w >= 0 && w < p.W_in) ? __ldg(zr + w) : 0.f;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < COP / 32; ++q) {
+          float m[32];
+#pragma unroll 1
+          for (int s = 0; s < 3; ++s) {
+            float v[32];
+            tmem_ld32(t_row + (uint32_t)(s * COP + q * 32), v);
+            if (MODE == TC_CONV2_ID) {
+              if (j < p.J) {
+                const __half* x = p.idn + ((((size_t)b * 23 + h) * 3 + s) * p.J + j) * (2 * COP);
+                add_pair32(x + q * 32, x + COP + q * 32, v);
+              }
+            } else if (MODE == TC_CONV2_Z) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const int c = q * 32 + i;
+                v[i] += __ldg(p.wd + c) * zq[s] + __ldg(p.wd + COP + c) * zq[s + 1] +
+                        __ldg(p.wd + 2 * COP + c) * zq[s + 2];
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) m[i] = s == 0 ? v[i] : fmaxf(m[i], v[i]);
+          }
+          const bool valid = j < p.Wo;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) m[i] = valid ? m[i] + __ldg(p.bias + q * 32 + i) : 0.f;
+          if (p.out_f32) {
+            if (valid)
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const int c = q * 32 + i;
+                if (c < p.Co) p.out_f32[(((size_t)b * p.Co + c) * 23 + h) * p.Wo + j] = m[i];
+              }
+          } else if (j / 3 < p.Jn) {
+            __half* o = p.out + ((((size_t)b * 23 + h) * 3 + (j % 3)) * p.Jn + j / 3) * (2 * COP);
+            store_pair32(o + q * 32, o + COP + q * 32, m);
+          }
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// block 0 conv1 (1 -> 32 channels, K = 6): not GEMM-shaped, CUDA cores.
+// z (B,23,W) fp32 -> v [B][24][3][J][64] fp16 pairs, v = selu(bn2(conv1(z)))
+// thread = one position, all 32 channels; weights broadcast from shared memory.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+block0_conv1_kernel(const float* __restrict__ z, const float* __restrict__ w /*[6][32]*/,
+                    const float* __restrict__ bias /*[32]*/, __half* __restrict__ out, int W, int J) {
+  __shared__ __align__(16) float s_w[6 * 32 + 32];
+  for (int i = threadIdx.x; i < 6 * 32; i += 128) s_w[i] = w[i];
+  if (threadIdx.x < 32) s_w[192 + threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  const int r = blockIdx.y / 3, phi = blockIdx.y % 3;   // output row 0..23
+  const int b = blockIdx.z;
+  if (j >= J) return;
+  const int pos = 3 * j + phi;
+  float v[32];
+  if (pos < W) {
+    float in[2][3];
+#pragma unroll
+    for (int dh = 0; dh < 2; ++dh) {
+      const int row = r + dh - 1;
+#pragma unroll
+      for (int dw = 0; dw < 3; ++dw) {
+        const int ww = pos + dw - 1;
+        in[dh][dw] = (row >= 0 && row < 23 && ww >= 0 && ww < W) ? __ldg(z + ((size_t)b * 23 + row) * W + ww) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 32; ++c) v[c] = s_w[192 + c];
+#pragma unroll
+    for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+      for (int dw = 0; dw < 3; ++dw) {
+        const float a = in[dh][dw];
+        const float4* wp = reinterpret_cast<const float4*>(s_w + (dh * 3 + dw) * 32);
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          float4 ww = wp[c4];
+          v[4 * c4] = fmaf(a, ww.x, v[4 * c4]);
+          v[4 * c4 + 1] = fmaf(a, ww.y, v[4 * c4 + 1]);
+          v[4 * c4 + 2] = fmaf(a, ww.z, v[4 * c4 + 2]);
+          v[4 * c4 + 3] = fmaf(a, ww.w, v[4 * c4 + 3]);
+        }
+      }
+#pragma unroll
+    for (int c = 0; c < 32; ++c) v[c] = selu_fast(v[c]);
+  } else {
+#pragma unroll
+    for (int c = 0; c < 32; ++c) v[c] = 0.f;
+  }
+  __half* o = out + ((((size_t)b * 24 + r) * 3 + phi) * J + j) * 64;
+  store_pair32(o, o + 32, v);
+}
+
+// ------------------------------------------------------------------------------------------
+// layout converters (stage entry points / tests only)
+// ------------------------------------------------------------------------------------------
+__global__ void pack_nchw_to_pairs_kernel(const float* __restrict__ in, __half* __restrict__ out, int C, int H,
+                                          int W, int J, int Cp, size_t total) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // over (b,h,phi,j,c<Cp)
+  if (i >= total) return;
+  int c = i % Cp;
+  size_t t = i / Cp;
+  int j = t % J; t /= J;
+  int phi = t % 3; t /= 3;
+  int h = t % H;
+  size_t b = t / H;
+  int w = 3 * j + phi;
+  float v = (c < C && w < W) ? in[((b * C + c) * H + h) * W + w] : 0.f;
+  __half hi, lo;
+  split_f16(clamp_h(v), hi, lo);
+  __half* o = out + ((((b * H + h) * 3 + phi) * J + j) * (size_t)(2 * Cp));
+  o[c] = hi;
+  o[Cp + c] = lo;
+}
+__global__ void unpack_pairs_to_nchw_kernel(const __half* __restrict__ in, float* __restrict__ out, int C, int H,
+                                            int W, int J, int Cp, size_t total) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // over (b,c,h,w)
+  if (i >= total) return;
+  int w = i % W;
+  size_t t = i / W;
+  int h = t % H; t /= H;
+  int c = t % C;
+  size_t b = t / C;
+  const __half* p = in + ((((b * H + h) * 3 + (w % 3)) * J + w / 3) * (size_t)(2 * Cp));
+  out[i] = __half2float(p[c]) + __half2float(p[Cp + c]);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_act_tmap(aasist_handle* h, CUtensorMap* m, const void* base, int Cp, int J, int H, int B) {
+  EncodeTiledFn fn = (EncodeTiledFn)h->tc->encode_fn;
+  cuuint64_t dims[5] = {(cuuint64_t)(2 * Cp), (cuuint64_t)J, 3, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[4];
+  strides[0] = (cuuint64_t)2 * Cp * 2;
+  strides[1] = strides[0] * J;
+  strides[2] = strides[1] * 3;
+  strides[3] = strides[2] * H;
+  cuuint32_t box[5] = {64, (cuuint32_t)kBoxRows, 1, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (Cp=%d J=%d H=%d B=%d)", (int)r, Cp, J, H, B);
+    return AASIST_E_CUDA;
+  }
+  return 0;
+}
+
+// weight image: per tap, SLABS slabs of [cop rows][128 B], rows 128-byte swizzled like a TMA SW128 tile
+//   cpi == 32: one slab, row = [w_hi(32) | w_lo(32)];  cpi == 64: slab 0 = w_hi(64), slab 1 = w_lo(64)
+static void put_tap(std::vector<uint8_t>& img, size_t tap_off, int cpi, int cop, int n, int k, float w) {
+  __half hi = __float2half_rn(w);
+  __half lo = __float2half_rn(w - __half2float(hi));
+  auto put = [&](size_t slab_off, int kk, __half v) {
+    int byte_in_row = kk * 2;
+    int chunk = byte_in_row / 16, within = byte_in_row % 16;
+    size_t off = slab_off + (size_t)n * 128 + (size_t)((chunk ^ (n & 7)) * 16 + within);
+    memcpy(&img[off], &v, 2);
+  };
+  if (cpi == 32) {
+    put(tap_off, k, hi);
+    put(tap_off, 32 + k, lo);
+  } else {
+    put(tap_off, k, hi);
+    put(tap_off + (size_t)cop * 128, k, lo);
+  }
+}
+
+static int upload_bytes(uint8_t** dst, const std::vector<uint8_t>& v) {
+  if (*dst) cudaFree(*dst);
+  *dst = nullptr;
+  AASIST_CUDA(cudaMalloc(dst, std::max<size_t>(v.size(), 16)));
+  AASIST_CUDA(cudaMemcpy(*dst, v.data(), v.size(), cudaMemcpyHostToDevice));
+  return 0;
+}
+static int upload_f(float** dst, const std::vector<float>& v) {
+  if (*dst) cudaFree(*dst);
+  *dst = nullptr;
+  AASIST_CUDA(cudaMalloc(dst, sizeof(float) * std::max<size_t>(v.size(), 4)));
+  AASIST_CUDA(cudaMemcpy(*dst, v.data(), sizeof(float) * v.size(), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+static inline int pad_ch(int c) { return c <= 32 ? 32 : 64; }
+
+static int pack_block_tc(aasist_handle* h, const std::string& pfx, int index, BlockTc& blk) {
+  const int ci = h->cfg.enc_channels[index][0], co = h->cfg.enc_channels[index][1];
+  blk.ci = ci;
+  blk.co = co;
+  blk.cpi = pad_ch(ci);
+  blk.cop = pad_ch(co);
+  blk.downsample = ci != co;
+  auto P = [&](const std::string& n) -> const std::vector<float>& { return h->params.at(pfx + n); };
+  const auto &w1 = P(".conv1.weight"), &b1 = P(".conv1.bias"), &w2 = P(".conv2.weight"), &b2 = P(".conv2.bias");
+  const auto &g = P(".bn2.weight"), &be = P(".bn2.bias"), &mu = P(".bn2.running_mean"), &var = P(".bn2.running_var");
+  std::vector<double> sc(co), sh(co);
+  for (int o = 0; o < co; ++o) {
+    sc[o] = (double)g[o] / sqrt((double)var[o] + kBnEps);
+    sh[o] = (double)be[o] - (double)mu[o] * sc[o];
+  }
+  int rc;
+  std::vector<float> bias1(blk.cop, 0.f), bias2(blk.cop, 0.f);
+  for (int o = 0; o < co; ++o) {
+    bias1[o] = (float)((double)b1[o] * sc[o] + sh[o]);
+    bias2[o] = b2[o];
+  }
+  if (index == 0) {
+    if (ci != 1 || blk.cop != 32) {
+      set_error("f16x3 path: encoder block 0 must be 1 -> <=32 channels");
+      return AASIST_E_INVALID;
+    }
+    std::vector<float> w(6 * 32, 0.f), wd(3 * 32, 0.f);
+    for (int o = 0; o < co; ++o)
+      for (int t = 0; t < 6; ++t) w[t * 32 + o] = (float)((double)w1[(size_t)o * 6 + t] * sc[o]);
+    if ((rc = upload_f(&blk.w1_f32, w))) return rc;
+    const auto &wdv = P(".conv_downsample.weight"), &bd = P(".conv_downsample.bias");
+    for (int o = 0; o < co; ++o) {
+      for (int t = 0; t < 3; ++t) wd[t * 32 + o] = wdv[(size_t)o * 3 + t];
+      bias2[o] = (float)((double)b2[o] + (double)bd[o]);
+    }
+    if ((rc = upload_f(&blk.wd_f32, wd))) return rc;
+  } else {
+    const int tap_bytes = (blk.cpi / 32) * blk.cop * 128;
+    std::vector<uint8_t> img((size_t)6 * tap_bytes, 0);
+    for (int o = 0; o < co; ++o)
+      for (int i = 0; i < ci; ++i)
+        for (int t = 0; t < 6; ++t)
+          put_tap(img, (size_t)t * tap_bytes, blk.cpi, blk.cop, o, i,
+                  (float)((double)w1[((size_t)o * ci + i) * 6 + t] * sc[o]));
+    blk.c1.wimg_bytes = (int)img.size();
+    if ((rc = upload_bytes(&blk.c1.wimg, img))) return rc;
+  }
+  if ((rc = upload_f(&blk.c1.bias, bias1))) return rc;
+  {
+    // conv2: K = cop (its input is this block's conv1 output)
+    const int tap_bytes = (blk.cop / 32) * blk.cop * 128;
+    const bool side = blk.downsample && index != 0;
+    if (side && blk.cpi != 32) {
+      set_error("f16x3 path: conv_downsample from a %d-channel input is not supported", ci);
+      return AASIST_E_INVALID;
+    }
+    std::vector<uint8_t> img((size_t)6 * tap_bytes + (side ? 3 * blk.cop * 128 : 0), 0);
+    for (int o = 0; o < co; ++o)
+      for (int i = 0; i < co; ++i)
+        for (int t = 0; t < 6; ++t)
+          put_tap(img, (size_t)t * tap_bytes, blk.cop, blk.cop, o, i, w2[((size_t)o * co + i) * 6 + t]);
+    if (side) {
+      const auto &wdv = P(".conv_downsample.weight"), &bd = P(".conv_downsample.bias");
+      for (int o = 0; o < co; ++o) {
+        for (int i = 0; i < ci; ++i)
+          for (int t = 0; t < 3; ++t)
+            put_tap(img, (size_t)6 * tap_bytes + (size_t)t * blk.cop * 128, 32, blk.cop, o, i,
+                    wdv[((size_t)o * ci + i) * 3 + t]);
+        bias2[o] = (float)((double)b2[o] + (double)bd[o]);
+      }
+    }
+    blk.c2.wimg_bytes = (int)img.size();
+    if ((rc = upload_bytes(&blk.c2.wimg, img))) return rc;
+  }
+  if ((rc = upload_f(&blk.c2.bias, bias2))) return rc;
+  return 0;
+}
+
+int tc_finalize(aasist_handle* h) {
+  if (!h->tc) h->tc = new TcState();
+  TcState* tc = h->tc;
+  cudaDeviceProp prop;
+  AASIST_CUDA(cudaGetDeviceProperties(&prop, h->device));
+  if (prop.major != 10) {
+    set_error("the f16x3 path needs an sm_100a GPU (tcgen05); device is sm_%d%d", prop.major, prop.minor);
+    return AASIST_E_CUDA;
+  }
+  tc->sm_count = prop.multiProcessorCount;
+  cudaDriverEntryPointQueryResult q;
+  AASIST_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &tc->encode_fn, cudaEnableDefault, &q));
+  if (!tc->encode_fn || q != cudaDriverEntryPointSuccess) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return AASIST_E_CUDA;
+  }
+  const char* enc_names[2] = {h->cfg.kind == AASIST_KIND_AASIST ? "encoder" : "encoder_T", "encoder_S"};
+  for (int e = 0; e < h->n_encoders; ++e)
+    for (int i = 0; i < 6; ++i) {
+      std::string p = std::string(enc_names[e]) + "." + std::to_string(i) + ".0";
+      int rc = pack_block_tc(h, p, i, tc->blocks[e][i]);
+      if (rc) return rc;
+    }
+  return 0;
+}
+
+void tc_destroy(aasist_handle* h) {
+  if (!h->tc) return;
+  for (int e = 0; e < 2; ++e)
+    for (int i = 0; i < 6; ++i) {
+      BlockTc& b = h->tc->blocks[e][i];
+      cudaFree(b.c1.wimg); cudaFree(b.c1.bias); cudaFree(b.c2.wimg); cudaFree(b.c2.bias);
+      cudaFree(b.w1_f32); cudaFree(b.wd_f32);
+    }
+  delete h->tc;
+  h->tc = nullptr;
+}
+
+struct TcPlan {
+  int W[7], J[7];         // W[i], J[i] = ceil(W[i]/3): width / phase length of block i's input
+  size_t z, mid, act;     // bytes per utterance
+};
+static void make_tc_plan(const aasist_handle* h, int L, TcPlan& pl) {
+  pl.W[0] = (L - h->taps + 1) / 3;
+  for (int i = 0; i < 6; ++i) pl.W[i + 1] = pl.W[i] / 3;
+  for (int i = 0; i < 7; ++i) pl.J[i] = (pl.W[i] + 2) / 3;
+  pl.z = sizeof(float) * (size_t)kSpecNodes * pl.W[0];
+  pl.mid = pl.act = 0;
+  for (int i = 0; i < 6; ++i) {
+    int cop = pad_ch(h->cfg.enc_channels[i][1]);
+    pl.mid = std::max(pl.mid, (size_t)24 * 3 * pl.J[i] * 2 * cop * 2);
+    pl.act = std::max(pl.act, (size_t)23 * 3 * pl.J[i + 1] * 2 * cop * 2);
+  }
+}
+static inline size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+size_t tc_workspace_bytes(const aasist_handle* h, int B, int L) {
+  TcPlan pl;
+  make_tc_plan(h, L, pl);
+  size_t nb = std::min(B, kChunkTc);
+  return al256(pl.z * nb) + al256(pl.mid * nb) + 2 * al256(pl.act * nb) + 1024;
+}
+
+template <int CPI, int COP, int MODE>
+static int launch_conv(aasist_handle* h, const char* name, const CUtensorMap& tmA, const CUtensorMap& tmS,
+                       ConvTcParams p, cudaStream_t st) {
+  constexpr int SLOT = (CPI / 32) * kSlabBytes;
+  const int budget = 227 * 1024 - 1024 /*align*/ - p.wimg_bytes - 256 /*barriers*/;
+  int n_slots = std::min(kMaxSlots, budget / SLOT);
+  if (n_slots < 2) {
+    set_error("conv_tc: not enough shared memory for the input ring (weights %d bytes)", p.wimg_bytes);
+    return AASIST_E_INVALID;
+  }
+  p.n_slots = n_slots;
+  size_t smem = 1024 + (size_t)p.wimg_bytes + (size_t)n_slots * SLOT + 256;
+  auto kern = conv_tc_kernel<CPI, COP, MODE>;
+  AASIST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int n_tiles = p.B * p.H_out * p.n_jt;
+  int grid = std::min(n_tiles, h->tc->sm_count);
+  {
+    LaunchSpan span(h, name, st);
+    kern<<<grid, kTcThreads, smem, st>>>(tmA, tmS, p);
+  }
+  AASIST_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// one residual block on the tensor-core path.
+//   in_pairs: block input in pair layout [nb][23][3][J][2*cpi]   (index >= 1)
+//   z:        block-0 input (nb,23,W) fp32                       (index == 0)
+//   out_pairs [nb][23][3][Jn][2*cop]  or  out_f32 (nb,co,23,Wo)
+static int run_block_tc(aasist_handle* h, int enc, int index, const __half* in_pairs, const float* z, int nb,
+                        int W, __half* mid, __half* out_pairs, float* out_f32, cudaStream_t st) {
+  const BlockTc& blk = h->tc->blocks[enc][index];
+  const int J = (W + 2) / 3, Wo = W / 3, Jn = (Wo + 2) / 3;
+  if (Wo < 1) {
+    set_error("encoder block %d input width %d < 3", index, W);
+    return AASIST_E_INVALID;
+  }
+  int rc;
+  CUtensorMap tmIn, tmMid;
+  memset(&tmIn, 0, sizeof(tmIn));
+  if ((rc = make_act_tmap(h, &tmMid, mid, blk.cop, J, 24, nb))) return rc;
+  if (index > 0 && (rc = make_act_tmap(h, &tmIn, in_pairs, blk.cpi, J, 23, nb))) return rc;
+  // ---- conv1 ----
+  if (index == 0) {
+    dim3 grid((J + 127) / 128, 24 * 3, nb);
+    LaunchSpan span(h, "block0_conv1", st);
+    block0_conv1_kernel<<<grid, 128, 0, st>>>(z, blk.w1_f32, blk.c1.bias, mid, W, J);
+  } else {
+    ConvTcParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = nb; p.H_out = 24; p.J = J; p.n_jt = (J + kTileJ - 1) / kTileJ; p.W_in = W; p.Co = blk.co;
+    p.bias = blk.c1.bias; p.out = mid; p.wimg = blk.c1.wimg; p.wimg_bytes = blk.c1.wimg_bytes;
+    if (blk.cpi == 32 && blk.cop == 32) rc = launch_conv<32, 32, TC_CONV1>(h, "conv1_tc", tmIn, tmIn, p, st);
+    else if (blk.cpi == 32 && blk.cop == 64) rc = launch_conv<32, 64, TC_CONV1>(h, "conv1_tc", tmIn, tmIn, p, st);
+    else if (blk.cpi == 64 && blk.cop == 64) rc = launch_conv<64, 64, TC_CONV1>(h, "conv1_tc", tmIn, tmIn, p, st);
+    else { set_error("f16x3 path: unsupported conv1 shape %d->%d", blk.ci, blk.co); rc = AASIST_E_INVALID; }
+    if (rc) return rc;
+  }
+  AASIST_CUDA(cudaGetLastError());
+  // ---- conv2 (+ identity / downsample) + max-pool ----
+  ConvTcParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = nb; p.H_out = 23; p.J = J; p.W_in = W; p.Co = blk.co; p.Wo = Wo; p.Jn = Jn;
+  p.n_jt = (std::max(J, std::min(3 * Jn, Wo + 2)) + kTileJ - 1) / kTileJ;
+  p.bias = blk.c2.bias; p.out = out_pairs; p.out_f32 = out_f32; p.wimg = blk.c2.wimg; p.wimg_bytes = blk.c2.wimg_bytes;
+  if (index == 0) {
+    p.z = z; p.wd = blk.wd_f32;
+    rc = launch_conv<32, 32, TC_CONV2_Z>(h, "conv2_tc", tmMid, tmMid, p, st);
+  } else if (!blk.downsample) {
+    p.idn = in_pairs;
+    if (blk.cop == 32) rc = launch_conv<32, 32, TC_CONV2_ID>(h, "conv2_tc", tmMid, tmMid, p, st);
+    else rc = launch_conv<64, 64, TC_CONV2_ID>(h, "conv2_tc", tmMid, tmMid, p, st);
+  } else {
+    if (blk.cop == 32) rc = launch_conv<32, 32, TC_CONV2_DS>(h, "conv2_tc", tmMid, tmIn, p, st);
+    else rc = launch_conv<64, 64, TC_CONV2_DS>(h, "conv2_tc", tmMid, tmIn, p, st);
+  }
+  return rc;
+}
+
+int tc_encode(aasist_handle* h, const float* x, int B, int L, float** enc_out, void* ws, cudaStream_t st) {
+  TcPlan pl;
+  make_tc_plan(h, L, pl);
+  const int nbmax = std::min(B, kChunkTc);
+  char* w = (char*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
+  float* z = (float*)w;
+  w += al256(pl.z * nbmax);
+  __half* mid = (__half*)w;
+  w += al256(pl.mid * nbmax);
+  __half* act[2];
+  act[0] = (__half*)w;
+  w += al256(pl.act * nbmax);
+  act[1] = (__half*)w;
+  const int C = h->cfg.enc_channels[5][1];
+  const size_t enc_per = (size_t)C * kSpecNodes * pl.W[6];
+  for (int b0 = 0; b0 < B; b0 += nbmax) {
+    const int nb = std::min(nbmax, B - b0);
+    int rc = launch_frontend_f32(h, x + (size_t)b0 * L, nb, L, z, st);
+    if (rc) return rc;
+    for (int e = 0; e < h->n_encoders; ++e) {
+      const __half* in = nullptr;
+      for (int i = 0; i < 6; ++i) {
+        __half* out = act[i & 1];
+        float* of32 = i == 5 ? enc_out[e] + (size_t)b0 * enc_per : nullptr;
+        if ((rc = run_block_tc(h, e, i, in, z, nb, pl.W[i], mid, out, of32, st))) return rc;
+        in = out;
+      }
+    }
+  }
+  return 0;
+}
+
+int tc_frontend_to_f32(aasist_handle* h, const float* x, int B, int L, float* out, void*, int64_t,
+                       cudaStream_t st) {
+  return launch_frontend_f32(h, x, B, L, out, st);   // the sinc stage of this path is still fp32
+}
+
+int tc_block_f32io(aasist_handle* h, int enc, int index, const float* in, int B, int W, float* out, void* ws,
+                   int64_t ws_bytes, cudaStream_t st) {
+  const BlockTc& blk = h->tc->blocks[enc][index];
+  const int J = (W + 2) / 3, Wo = W / 3, Jn = (Wo + 2) / 3;
+  size_t in_b = al256((size_t)B * 23 * 3 * J * 2 * blk.cpi * 2), mid_b = al256((size_t)B * 24 * 3 * J * 2 * blk.cop * 2),
+         out_b = al256((size_t)B * 23 * 3 * Jn * 2 * blk.cop * 2);
+  if (!ws || (size_t)ws_bytes < in_b + mid_b + out_b + 1024) {
+    set_error("aasist_encoder_block (f16x3): workspace needs %zu bytes", in_b + mid_b + out_b + 1024);
+    return AASIST_E_WORKSPACE;
+  }
+  char* w = (char*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
+  __half* pin = (__half*)w;
+  __half* mid = (__half*)(w + in_b);
+  __half* pout = (__half*)(w + in_b + mid_b);
+  if (index > 0) {
+    size_t total = (size_t)B * 23 * 3 * J * blk.cpi;
+    LaunchSpan span(h, "pack_pairs", st);
+    pack_nchw_to_pairs_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, pin, blk.ci, 23, W, J, blk.cpi, total);
+  }
+  int rc = run_block_tc(h, enc, index, pin, in, B, W, mid, pout, nullptr, st);
+  if (rc) return rc;
+  size_t total = (size_t)B * blk.co * 23 * Wo;
+  {
+    LaunchSpan span(h, "unpack_pairs", st);
+    unpack_pairs_to_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(pout, out, blk.co, 23, Wo, Jn, blk.cop, total);
+  }
+  AASIST_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace aasist

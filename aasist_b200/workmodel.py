@@ -35,10 +35,8 @@ def kernel_flops(name: str, kernel: str, batch: int, length: int = 64600) -> flo
         macs = sum(m[f"enc{i}.conv1"] for i in range(1, 6))
     elif kernel.startswith("conv2"):
         macs = sum(m[f"enc{i}.conv2"] + m[f"enc{i}.ds"] for i in range(6))
-    elif kernel.startswith("block0"):
-        macs = m["enc0.conv1"] + m["enc0.conv2"] + m["enc0.ds"]
-    elif kernel.startswith("block"):
-        macs = sum(m[f"enc{i}.conv1"] + m[f"enc{i}.conv2"] + m[f"enc{i}.ds"] for i in range(1, 6))
+    elif kernel.startswith("block0_conv1"):
+        macs = m["enc0.conv1"]
     elif "graph" in kernel:
         macs = m["graph"]
     else:

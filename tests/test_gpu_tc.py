@@ -1,0 +1,93 @@
+"""Tensor-core path (precision="f16x3": tcgen05, fp16 hi/lo split operands, fp32 accumulate in TMEM)
+against the CPU oracle / golden fixtures.  Tolerance on logits: north_star allows 1e-3 for
+reduced-precision tensor paths; the split scheme is expected (CPU emulation) to reach ~1e-5."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import aasist_oracle as O
+from tests.util import golden_input, load_golden, pools_of
+
+pytestmark = pytest.mark.gpu
+
+TC_LOGIT_TOL = 2e-4
+CASES = [("AASIST", "white"), ("AASIST", "speech"), ("AASIST", "speech16k"), ("AASIST", "speech96k"),
+         ("AASIST-L", "white"), ("AASIST-L", "speech"), ("AASIST-L", "speech16k"), ("AASIST-L", "speech96k"),
+         ("RawGAT-ST", "white"), ("RawGAT-ST", "speech")]
+
+
+def _g():
+    from tests import gpu_util
+    return gpu_util
+
+
+@pytest.mark.parametrize("name", ["AASIST", "AASIST-L"])
+def test_tc_encoder_blocks_stagewise(name):
+    g = _g()
+    x = O.speech_like(2, 64600, 4)
+    taps = g.oracle_taps(name, x)
+    m = g.native_model(name, "f16x3")
+    f = O.CONFIGS[name]["filts"]
+    chans = [f[1], f[2], f[3], f[4], f[4], f[4]]
+    inp = taps["frontend"]
+    report = {}
+    for i in range(6):
+        ref = taps[f"encoder.{i}"]
+        out = g.stage_block(m, 0, i, inp.to(g.DEV), chans[i][1])
+        err = (out.cpu() - ref).abs().max().item()
+        report[i] = err / max(1.0, ref.abs().max().item())
+        inp = ref
+    print(json.dumps({"model": name, "block_rel_err": report}))
+    for i, e in report.items():
+        # fp16-pair operands: ~2^-21 relative per product, fp32 accumulation
+        assert e <= 2e-5, (i, report)
+
+
+@pytest.mark.parametrize("name,tag", CASES)
+def test_tc_full_forward_against_golden(name, tag):
+    g = _g()
+    gold, meta = load_golden(name, tag)
+    x = golden_input(meta).to(g.DEV)
+    m = g.native_model(name, "f16x3")
+    m.record_topk = True
+    try:
+        last_hidden, output = m(x)
+        torch.cuda.synchronize()
+        pools = g.split_pools(m.last_topk, m.last_pool_weights, m.topk_layout(meta["L"]))
+    finally:
+        m.record_topk = False
+    err = np.abs(output.cpu().numpy() - gold["output"]).max()
+    herr = np.abs(last_hidden.cpu().numpy() - gold["last_hidden"]).max()
+    rep = g.check_pools(pools, gold, pools_of(name))
+    print(json.dumps({"case": f"{name}/{tag}", "logit_err": float(err), "hidden_err": float(herr), "pools": rep}))
+    assert err <= TC_LOGIT_TOL and herr <= TC_LOGIT_TOL, (err, herr)
+    for p, r in rep.items():
+        assert r["weights_err"] <= 2e-4, (p, r)
+        assert r["mismatch_outside_near_ties"] == 0, (p, r)
+
+
+def test_tc_batch_invariance_and_fp32_agreement():
+    g = _g()
+    m = g.native_model("AASIST", "f16x3")
+    m32 = g.native_model("AASIST", "fp32")
+    x = O.speech_like(5, 64600, 21).to(g.DEV)
+    out = m(x)[1]
+    assert torch.equal(out, m(x)[1])                                   # deterministic
+    single = torch.cat([m(x[i:i + 1])[1] for i in range(5)])
+    assert torch.equal(out, single)                                    # shard invariance
+    assert (out - m32(x)[1]).abs().max().item() <= TC_LOGIT_TOL
+    m(torch.zeros(1, 2315, device=g.DEV))                              # shortest valid length
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 2000, device=g.DEV))
+
+
+def test_tc_larger_batch_crosses_chunk_boundary():
+    g = _g()
+    m = g.native_model("AASIST-L", "f16x3")
+    x = O.white_noise(3, 64600, 5).to(g.DEV)
+    big = x.repeat(50, 1)                                              # 150 utterances > one 128-chunk
+    out = m(big)[1]
+    ref = m(x)[1]
+    assert torch.equal(out.view(50, 3, 2), ref.unsqueeze(0).expand(50, 3, 2))
