@@ -274,7 +274,7 @@ class _NativeModel(nn.Module):
         return int(_lib.load().aasist_launch_count(self._handle)) if self._handle is not None else 0
 
 
-DEFAULT_PRECISION = "fp32"
+DEFAULT_PRECISION = "f16x3"
 
 
 class Model(_NativeModel):
