@@ -28,7 +28,8 @@ using namespace ptx;
 constexpr int kTileJ = 128;                 // pooled columns per CTA tile (UMMA M)
 constexpr int kBoxRows = kTileJ + 2;        // rows j0-1 .. j0+128
 constexpr int kSlabBytes = 17 * 1024;       // 130 rows x 128 B, rounded up to the 1024-B swizzle atom
-constexpr int kTcThreads = 192;
+constexpr int kEpiWarps = 8;                // two warps per TMEM lane quadrant (column halves)
+constexpr int kTcThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxSlots = 8;
 constexpr int kChunkTc = 128;               // utterances per encoder pass (bounds scratch)
 
@@ -37,6 +38,7 @@ enum { TC_CONV1 = 0, TC_CONV2_ID = 1, TC_CONV2_DS = 2, TC_CONV2_Z = 3 };
 struct ConvTcParams {
   int B, H_out, J, n_jt, W_in, Co, Wo, Jn;
   int n_slots;
+  int dbg;                 // timing experiments only (AASIST_TC_DEBUG): 1 = hi*hi product only, 2 = no epilogue math
   const float* bias;       // [COP]
   __half* out;             // CONV1: [B][24][3][J][2*COP]; CONV2: [B][23][3][Jn][2*COP]
   float* out_f32;          // last block: (B,Co,23,Wo) fp32 NCHW (then `out` is unused)
@@ -66,43 +68,66 @@ struct TcState {
 };
 
 __device__ __forceinline__ float selu_fast(float v) {
-  // negative branch through MUFU.EX2: |abs error| <= ~2.5e-7 (same order as the fp16-pair
-  // representation error of the stored activation)
-  return v > 0.f ? kSeluScale * v : (kSeluScale * kSeluAlpha) * (exp2f(v * 1.4426950408889634f) - 1.f);
+  // scale*max(v,0) + min(0, scale*alpha*(2^(v*log2e) - 1)); the negative branch goes through
+  // MUFU.EX2: |abs error| <= ~2.5e-7, the same order as the fp16-pair representation error
+  const float e = exp2f(v * 1.4426950408889634f);
+  const float n = fminf(fmaf(e, kSeluScale * kSeluAlpha, -(kSeluScale * kSeluAlpha)), 0.f);
+  return fmaf(fmaxf(v, 0.f), kSeluScale, n);
 }
-__device__ __forceinline__ float clamp_h(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
 
-// store 32 fp32 channels as hi (64 B) and lo (64 B) fp16 vectors
-__device__ __forceinline__ void store_pair32(__half* hi_dst, __half* lo_dst, const float (&v)[32]) {
-  uint32_t hw[16], lw[16];
+// (a,b) fp32 -> packed hi half2 and lo half2 (a ~= hi+lo to 2^-22), saturating at the fp16 range
+__device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  a = fminf(fmaxf(a, -65504.f), 65504.f);
+  b = fminf(fmaxf(b, -65504.f), 65504.f);
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 f = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// store 16 fp32 channels as hi (32 B) and lo (32 B) fp16 vectors
+__device__ __forceinline__ void store_pair16(__half* hi_dst, __half* lo_dst, const float (&v)[16]) {
+  uint32_t hw[8], lw[8];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    __half h0, l0, h1, l1;
-    split_f16(clamp_h(v[2 * i]), h0, l0);
-    split_f16(clamp_h(v[2 * i + 1]), h1, l1);
-    hw[i] = pack_h2(h0, h1);
-    lw[i] = pack_h2(l0, l1);
-  }
+  for (int i = 0; i < 8; ++i) split_pack2(v[2 * i], v[2 * i + 1], hw[i], lw[i]);
   uint4* hd = reinterpret_cast<uint4*>(hi_dst);
   uint4* ld = reinterpret_cast<uint4*>(lo_dst);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    hd[i] = make_uint4(hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]);
-    ld[i] = make_uint4(lw[4 * i], lw[4 * i + 1], lw[4 * i + 2], lw[4 * i + 3]);
-  }
+  hd[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+  hd[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+  ld[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+  ld[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
 }
-// v[i] += float(hi[i]) + float(lo[i]) for 32 channels
-__device__ __forceinline__ void add_pair32(const __half* hi_src, const __half* lo_src, float (&v)[32]) {
-  const uint4* hs = reinterpret_cast<const uint4*>(hi_src);
-  const uint4* ls = reinterpret_cast<const uint4*>(lo_src);
+__device__ __forceinline__ void store_pair32(__half* hi_dst, __half* lo_dst, const float (&v)[32]) {
+  float a[16], b[16];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    uint4 a = __ldg(hs + i), b = __ldg(ls + i);
-    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+  for (int i = 0; i < 16; ++i) { a[i] = v[i]; b[i] = v[16 + i]; }
+  store_pair16(hi_dst, lo_dst, a);
+  store_pair16(hi_dst + 16, lo_dst + 16, b);
+}
+struct Pair16 { uint4 h[2], l[2]; };   // 16 channels of an activation: hi and lo fp16 vectors
+__device__ __forceinline__ Pair16 load_pair16(const __half* hi_src, const __half* lo_src) {
+  Pair16 p;
+  p.h[0] = __ldg(reinterpret_cast<const uint4*>(hi_src));
+  p.h[1] = __ldg(reinterpret_cast<const uint4*>(hi_src) + 1);
+  p.l[0] = __ldg(reinterpret_cast<const uint4*>(lo_src));
+  p.l[1] = __ldg(reinterpret_cast<const uint4*>(lo_src) + 1);
+  return p;
+}
+__device__ __forceinline__ Pair16 zero_pair16() {
+  Pair16 p;
+  p.h[0] = p.h[1] = p.l[0] = p.l[1] = make_uint4(0, 0, 0, 0);
+  return p;
+}
+// v[i] += float(hi[i]) + float(lo[i])
+__device__ __forceinline__ void add_pair16(const Pair16& p, float (&v)[16]) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const uint32_t aw[4] = {p.h[i].x, p.h[i].y, p.h[i].z, p.h[i].w};
+    const uint32_t bw[4] = {p.l[i].x, p.l[i].y, p.l[i].z, p.l[i].w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      float2 fa = __half22float2(*reinterpret_cast<const __half2*>(&aw[k]));
-      float2 fb = __half22float2(*reinterpret_cast<const __half2*>(&bw[k]));
+      const float2 fa = __half22float2(*reinterpret_cast<const __half2*>(&aw[k]));
+      const float2 fb = __half22float2(*reinterpret_cast<const __half2*>(&bw[k]));
       v[8 * i + 2 * k] += fa.x + fb.x;
       v[8 * i + 2 * k + 1] += fa.y + fb.y;
     }
@@ -125,6 +150,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr uint32_t IDESC = umma_idesc_f16(128, COP);
   constexpr int N_MAIN = 6;
   constexpr int N_SIDE = (MODE == TC_CONV2_DS) ? 3 : 0;
+  constexpr int NCH = COP / 32;                      // 16-column chunks per epilogue warp (it owns COP/2 columns)
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -151,7 +177,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);     // one arrival per epilogue warp
+      mbar_init(&tempty[i], kEpiWarps);   // one arrival per epilogue warp
     }
     fence_barrier_init();
     prefetch_tensormap(&tmA);
@@ -192,142 +218,200 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ==================================
-    if (lane == 0) {
-      int slot = 0;
-      uint32_t phase = 0;
-      int tcount = 0;
-      const uint32_t w_base = smem_u32(s_w);
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
-        const int buf = tcount & 1;
-        mbar_wait(&tempty[buf], ((tcount >> 1) & 1) ^ 1);
+    // the whole warp walks the (warp-uniform) schedule; one elected lane issues tcgen05 ops
+    int slot = 0;
+    uint32_t phase = 0;
+    int tcount = 0;
+    const uint32_t w_base = smem_u32(s_w);
+    const bool leader = elect_one();
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
+      const int buf = tcount & 1;
+      mbar_wait(&tempty[buf], ((tcount >> 1) & 1) ^ 1);
+      tc_fence_after_sync();
+      uint32_t started = 0;   // bit s: accumulator s already holds a partial sum
+      for (int it = 0; it < N_MAIN + N_SIDE; ++it) {
+        mbar_wait(&full[slot], phase);
         tc_fence_after_sync();
-        uint32_t started = 0;   // bit s: accumulator s already holds a partial sum
-        for (int it = 0; it < N_MAIN + N_SIDE; ++it) {
-          mbar_wait(&full[slot], phase);
-          tc_fence_after_sync();
-          const uint32_t a_slot = smem_u32(s_ring + (size_t)slot * SLOT_BYTES);
-          const bool side = it >= N_MAIN;
-          const int dh = side ? 0 : it / 3, phi = side ? it - N_MAIN : it % 3;
+        const uint32_t a_slot = smem_u32(s_ring) + (uint32_t)slot * SLOT_BYTES;
+        const bool side = it >= N_MAIN;
+        const int dh = side ? 0 : it / 3, phi = side ? it - N_MAIN : it % 3;
+        if (leader) {
 #pragma unroll
           for (int s = 0; s < 3; ++s) {
             const int d = (phi - s + 3) % 3;              // input phase phi serves pool phase s via tap dw
             const int dw = d == 0 ? 1 : (d == 1 ? 2 : 0);
-            const int pp = s + dw - 1;                    // input position offset in units of phase steps
+            const int pp = s + dw - 1;                    // offset of the tap in units of phase steps
             const int shift = pp < 0 ? -1 : (pp > 2 ? 1 : 0);
             const uint32_t a_row = a_slot + (uint32_t)(1 + shift) * 128;
             const uint32_t d_tmem = tmem_base + (uint32_t)((buf * 3 + s) * COP);
             if (!side) {
               const uint32_t wt = w_base + (uint32_t)((dh * 3 + dw) * TAP_BYTES);
+              const uint64_t a_hi = umma_desc_sw128(a_row);
+              const uint64_t a_lo = umma_desc_sw128((SLABS == 1) ? a_row + 64 : a_row + kSlabBytes);
+              const uint64_t w_hi = umma_desc_sw128(wt);
+              const uint64_t w_lo = umma_desc_sw128((SLABS == 1) ? wt + 64 : wt + COP * 128);
 #pragma unroll
-              for (int kc = 0; kc < KC; ++kc) {
-                const uint32_t a_hi = a_row + kc * 32;
-                const uint32_t a_lo = (SLABS == 1) ? a_row + 64 + kc * 32 : a_row + kSlabBytes + kc * 32;
-                const uint32_t w_hi = wt + kc * 32;
-                const uint32_t w_lo = (SLABS == 1) ? wt + 64 + kc * 32 : wt + COP * 128 + kc * 32;
-                umma_f16(d_tmem, umma_desc_sw128(a_hi), umma_desc_sw128(w_hi), IDESC, (started >> s) & 1);
-                started |= 1u << s;
-                umma_f16(d_tmem, umma_desc_sw128(a_lo), umma_desc_sw128(w_hi), IDESC, 1);
-                umma_f16(d_tmem, umma_desc_sw128(a_hi), umma_desc_sw128(w_lo), IDESC, 1);
+              for (int kc = 0; kc < KC; ++kc) {           // +32 B per K chunk == +2 in the descriptor
+                umma_f16(d_tmem, a_hi + 2 * kc, w_hi + 2 * kc, IDESC, (kc > 0) | ((started >> s) & 1));
+                if (!(p.dbg & 1)) {
+                  umma_f16(d_tmem, a_lo + 2 * kc, w_hi + 2 * kc, IDESC, 1);
+                  umma_f16(d_tmem, a_hi + 2 * kc, w_lo + 2 * kc, IDESC, 1);
+                }
               }
             } else {
               const uint32_t wt = w_base + (uint32_t)(6 * TAP_BYTES + dw * SIDE_TAP_BYTES);
+              const uint64_t a_hi = umma_desc_sw128(a_row), a_lo = umma_desc_sw128(a_row + 64);
+              const uint64_t w_hi = umma_desc_sw128(wt), w_lo = umma_desc_sw128(wt + 64);
 #pragma unroll
               for (int kc = 0; kc < 2; ++kc) {
-                const uint32_t a_hi = a_row + kc * 32, a_lo = a_row + 64 + kc * 32;
-                const uint32_t w_hi = wt + kc * 32, w_lo = wt + 64 + kc * 32;
-                umma_f16(d_tmem, umma_desc_sw128(a_hi), umma_desc_sw128(w_hi), IDESC, 1);
-                umma_f16(d_tmem, umma_desc_sw128(a_lo), umma_desc_sw128(w_hi), IDESC, 1);
-                umma_f16(d_tmem, umma_desc_sw128(a_hi), umma_desc_sw128(w_lo), IDESC, 1);
+                umma_f16(d_tmem, a_hi + 2 * kc, w_hi + 2 * kc, IDESC, 1);
+                umma_f16(d_tmem, a_lo + 2 * kc, w_hi + 2 * kc, IDESC, 1);
+                umma_f16(d_tmem, a_hi + 2 * kc, w_lo + 2 * kc, IDESC, 1);
               }
             }
           }
           umma_commit(&empty[slot]);                      // slot reusable once these MMAs retire
-          if (++slot == p.n_slots) { slot = 0; phase ^= 1; }
         }
-        umma_commit(&tfull[buf]);                         // accumulators of this tile complete
+        started = 7;
+        __syncwarp();
+        if (++slot == p.n_slots) { slot = 0; phase ^= 1; }
       }
+      if (leader) umma_commit(&tfull[buf]);               // accumulators of this tile complete
+      __syncwarp();
     }
   } else {
-    // =============================== epilogue (warps 2..5) ========================
-    const int quad = warp & 3;                            // TMEM lane quadrant this warp may access
-    const int r = quad * 32 + lane;                       // accumulator row == pooled column offset
+    // =============================== epilogue (warps 2..9) ========================
+    // warp -> (TMEM lane quadrant, column half): thread = one pooled column j, COP/2 channels
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int r = quad * 32 + lane;
+    const int col0 = half * (COP / 2);
+    float bias[NCH][16];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) bias[c][i] = __ldg(p.bias + col0 + c * 16 + i);
+    float wdr[(MODE == TC_CONV2_Z) ? 3 : 1][NCH][16];
+    if (MODE == TC_CONV2_Z) {
+#pragma unroll
+      for (int t = 0; t < 3; ++t)
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) wdr[t][c][i] = __ldg(p.wd + t * COP + col0 + c * 16 + i);
+    }
     int tcount = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
       const int h = t % p.H_out, jt = (t / p.H_out) % p.n_jt, b = t / (p.H_out * p.n_jt);
       const int buf = tcount & 1;
       const int j = jt * kTileJ + r;
-      mbar_wait(&tfull[buf], (tcount >> 1) & 1);
-      tc_fence_after_sync();
-      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 3 * COP);
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 3 * COP + col0);
       if (MODE == TC_CONV1) {
+        mbar_wait(&tfull[buf], (tcount >> 1) & 1);
+        tc_fence_after_sync();
         // out[b][h][s][j][:] = selu(acc + b1), zero beyond the valid width
-#pragma unroll 1
+        uint32_t acc[3][NCH][16];
+#pragma unroll
+        for (int s = 0; s < 3; ++s)
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) tmem_ld16_async(t_row + (uint32_t)(s * COP + c * 16), acc[s][c]);
+#pragma unroll
+        for (int s = 0; s < 3; ++s)
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) tmem_ld_wait16(acc[s][c]);
+        // the accumulators are in registers: release the TMEM buffer before the math / stores
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[buf]);
+        if (p.dbg & 2) continue;
+#pragma unroll
         for (int s = 0; s < 3; ++s) {
+          const bool valid = 3 * j + s < p.W_in;
 #pragma unroll
-          for (int q = 0; q < COP / 32; ++q) {
-            float v[32];
-            tmem_ld32(t_row + (uint32_t)(s * COP + q * 32), v);
-            const bool valid = 3 * j + s < p.W_in;
+          for (int c = 0; c < NCH; ++c) {
+            float v[16];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = valid ? selu_fast(v[i] + __ldg(p.bias + q * 32 + i)) : 0.f;
+            for (int i = 0; i < 16; ++i)
+              v[i] = valid ? selu_fast(__uint_as_float(acc[s][c][i]) + bias[c][i]) : 0.f;
             if (j < p.J) {
-              __half* o = p.out + ((((size_t)b * 24 + h) * 3 + s) * p.J + j) * (2 * COP);
-              store_pair32(o + q * 32, o + COP + q * 32, v);
+              __half* o = p.out + ((((size_t)b * 24 + h) * 3 + s) * p.J + j) * (2 * COP) + col0 + c * 16;
+              store_pair16(o, o + COP, v);
             }
           }
         }
       } else {
+        // operands that do not depend on the accumulators are fetched before waiting for them
+        Pair16 idn[(MODE == TC_CONV2_ID) ? 3 : 1][NCH];
         float zq[5];
-        if (MODE == TC_CONV2_Z) {
+        if (MODE == TC_CONV2_ID) {
+#pragma unroll
+          for (int s = 0; s < 3; ++s)
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+              if (j < p.J) {
+                const __half* x = p.idn + ((((size_t)b * 23 + h) * 3 + s) * p.J + j) * (2 * COP) + col0 + c * 16;
+                idn[s][c] = load_pair16(x, x + COP);
+              } else {
+                idn[s][c] = zero_pair16();
+              }
+            }
+        } else if (MODE == TC_CONV2_Z) {
           const float* zr = p.z + ((size_t)b * 23 + h) * p.W_in;
 #pragma unroll
           for (int i = 0; i < 5; ++i) {
-            int w = 3 * j - 1 + i;
+            const int w = 3 * j - 1 + i;
             zq[i] = (w >= 0 && w < p.W_in) ? __ldg(zr + w) : 0.f;
           }
         }
+        mbar_wait(&tfull[buf], (tcount >> 1) & 1);
+        tc_fence_after_sync();
+        const bool valid = j < p.Wo;
+        uint32_t acc[3][NCH][16];
 #pragma unroll
-        for (int q = 0; q < COP / 32; ++q) {
-          float m[32];
-#pragma unroll 1
+        for (int s = 0; s < 3; ++s)
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) tmem_ld16_async(t_row + (uint32_t)(s * COP + c * 16), acc[s][c]);
+#pragma unroll
+        for (int s = 0; s < 3; ++s)
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) tmem_ld_wait16(acc[s][c]);
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[buf]);
+        if (p.dbg & 2) continue;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          float m[16];
+#pragma unroll
           for (int s = 0; s < 3; ++s) {
-            float v[32];
-            tmem_ld32(t_row + (uint32_t)(s * COP + q * 32), v);
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[s][c][i]);
             if (MODE == TC_CONV2_ID) {
-              if (j < p.J) {
-                const __half* x = p.idn + ((((size_t)b * 23 + h) * 3 + s) * p.J + j) * (2 * COP);
-                add_pair32(x + q * 32, x + COP + q * 32, v);
-              }
+              add_pair16(idn[s][c], v);
             } else if (MODE == TC_CONV2_Z) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const int c = q * 32 + i;
-                v[i] += __ldg(p.wd + c) * zq[s] + __ldg(p.wd + COP + c) * zq[s + 1] +
-                        __ldg(p.wd + 2 * COP + c) * zq[s + 2];
-              }
+              for (int i = 0; i < 16; ++i)
+                v[i] += wdr[0][c][i] * zq[s] + wdr[1][c][i] * zq[s + 1] + wdr[2][c][i] * zq[s + 2];
             }
 #pragma unroll
-            for (int i = 0; i < 32; ++i) m[i] = s == 0 ? v[i] : fmaxf(m[i], v[i]);
+            for (int i = 0; i < 16; ++i) m[i] = s == 0 ? v[i] : fmaxf(m[i], v[i]);
           }
-          const bool valid = j < p.Wo;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) m[i] = valid ? m[i] + __ldg(p.bias + q * 32 + i) : 0.f;
+          for (int i = 0; i < 16; ++i) m[i] = valid ? m[i] + bias[c][i] : 0.f;
           if (p.out_f32) {
             if (valid)
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const int c = q * 32 + i;
-                if (c < p.Co) p.out_f32[(((size_t)b * p.Co + c) * 23 + h) * p.Wo + j] = m[i];
+              for (int i = 0; i < 16; ++i) {
+                const int ch = col0 + c * 16 + i;
+                if (ch < p.Co) p.out_f32[(((size_t)b * p.Co + ch) * 23 + h) * p.Wo + j] = m[i];
               }
           } else if (j / 3 < p.Jn) {
-            __half* o = p.out + ((((size_t)b * 23 + h) * 3 + (j % 3)) * p.Jn + j / 3) * (2 * COP);
-            store_pair32(o + q * 32, o + COP + q * 32, m);
+            __half* o = p.out + ((((size_t)b * 23 + h) * 3 + (j % 3)) * p.Jn + j / 3) * (2 * COP) + col0 + c * 16;
+            store_pair16(o, o + COP, m);
           }
         }
       }
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[buf]);
     }
   }
   tc_fence_before_sync();
@@ -397,6 +481,7 @@ block0_conv1_kernel(const float* __restrict__ z, const float* __restrict__ w /*[
 // ------------------------------------------------------------------------------------------
 // layout converters (stage entry points / tests only)
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float clamp_h(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
 __global__ void pack_nchw_to_pairs_kernel(const float* __restrict__ in, __half* __restrict__ out, int C, int H,
                                           int W, int J, int Cp, size_t total) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // over (b,h,phi,j,c<Cp)
@@ -633,6 +718,10 @@ size_t tc_workspace_bytes(const aasist_handle* h, int B, int L) {
   return al256(pl.z * nb) + al256(pl.mid * nb) + 2 * al256(pl.act * nb) + 1024;
 }
 
+static const char* kConvNames[2][6] = {
+    {"enc0.conv1", "enc1.conv1_tc", "enc2.conv1_tc", "enc3.conv1_tc", "enc4.conv1_tc", "enc5.conv1_tc"},
+    {"enc0.conv2_tc", "enc1.conv2_tc", "enc2.conv2_tc", "enc3.conv2_tc", "enc4.conv2_tc", "enc5.conv2_tc"}};
+
 template <int CPI, int COP, int MODE>
 static int launch_conv(aasist_handle* h, const char* name, const CUtensorMap& tmA, const CUtensorMap& tmS,
                        ConvTcParams p, cudaStream_t st) {
@@ -644,6 +733,14 @@ static int launch_conv(aasist_handle* h, const char* name, const CUtensorMap& tm
     return AASIST_E_INVALID;
   }
   p.n_slots = n_slots;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("AASIST_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.dbg = dbg;
+    static int slots_override = -1;
+    if (slots_override < 0) { const char* e = getenv("AASIST_TC_SLOTS"); slots_override = e ? atoi(e) : 0; }
+    if (slots_override >= 2 && slots_override <= n_slots) p.n_slots = n_slots = slots_override;
+  }
   size_t smem = 1024 + (size_t)p.wimg_bytes + (size_t)n_slots * SLOT + 256;
   auto kern = conv_tc_kernel<CPI, COP, MODE>;
   AASIST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -677,16 +774,16 @@ static int run_block_tc(aasist_handle* h, int enc, int index, const __half* in_p
   // ---- conv1 ----
   if (index == 0) {
     dim3 grid((J + 127) / 128, 24 * 3, nb);
-    LaunchSpan span(h, "block0_conv1", st);
+    LaunchSpan span(h, kConvNames[0][0], st);
     block0_conv1_kernel<<<grid, 128, 0, st>>>(z, blk.w1_f32, blk.c1.bias, mid, W, J);
   } else {
     ConvTcParams p;
     memset(&p, 0, sizeof(p));
     p.B = nb; p.H_out = 24; p.J = J; p.n_jt = (J + kTileJ - 1) / kTileJ; p.W_in = W; p.Co = blk.co;
     p.bias = blk.c1.bias; p.out = mid; p.wimg = blk.c1.wimg; p.wimg_bytes = blk.c1.wimg_bytes;
-    if (blk.cpi == 32 && blk.cop == 32) rc = launch_conv<32, 32, TC_CONV1>(h, "conv1_tc", tmIn, tmIn, p, st);
-    else if (blk.cpi == 32 && blk.cop == 64) rc = launch_conv<32, 64, TC_CONV1>(h, "conv1_tc", tmIn, tmIn, p, st);
-    else if (blk.cpi == 64 && blk.cop == 64) rc = launch_conv<64, 64, TC_CONV1>(h, "conv1_tc", tmIn, tmIn, p, st);
+    if (blk.cpi == 32 && blk.cop == 32) rc = launch_conv<32, 32, TC_CONV1>(h, kConvNames[0][index], tmIn, tmIn, p, st);
+    else if (blk.cpi == 32 && blk.cop == 64) rc = launch_conv<32, 64, TC_CONV1>(h, kConvNames[0][index], tmIn, tmIn, p, st);
+    else if (blk.cpi == 64 && blk.cop == 64) rc = launch_conv<64, 64, TC_CONV1>(h, kConvNames[0][index], tmIn, tmIn, p, st);
     else { set_error("f16x3 path: unsupported conv1 shape %d->%d", blk.ci, blk.co); rc = AASIST_E_INVALID; }
     if (rc) return rc;
   }
@@ -699,14 +796,14 @@ static int run_block_tc(aasist_handle* h, int enc, int index, const __half* in_p
   p.bias = blk.c2.bias; p.out = out_pairs; p.out_f32 = out_f32; p.wimg = blk.c2.wimg; p.wimg_bytes = blk.c2.wimg_bytes;
   if (index == 0) {
     p.z = z; p.wd = blk.wd_f32;
-    rc = launch_conv<32, 32, TC_CONV2_Z>(h, "conv2_tc", tmMid, tmMid, p, st);
+    rc = launch_conv<32, 32, TC_CONV2_Z>(h, kConvNames[1][index], tmMid, tmMid, p, st);
   } else if (!blk.downsample) {
     p.idn = in_pairs;
-    if (blk.cop == 32) rc = launch_conv<32, 32, TC_CONV2_ID>(h, "conv2_tc", tmMid, tmMid, p, st);
-    else rc = launch_conv<64, 64, TC_CONV2_ID>(h, "conv2_tc", tmMid, tmMid, p, st);
+    if (blk.cop == 32) rc = launch_conv<32, 32, TC_CONV2_ID>(h, kConvNames[1][index], tmMid, tmMid, p, st);
+    else rc = launch_conv<64, 64, TC_CONV2_ID>(h, kConvNames[1][index], tmMid, tmMid, p, st);
   } else {
-    if (blk.cop == 32) rc = launch_conv<32, 32, TC_CONV2_DS>(h, "conv2_tc", tmMid, tmIn, p, st);
-    else rc = launch_conv<64, 64, TC_CONV2_DS>(h, "conv2_tc", tmMid, tmIn, p, st);
+    if (blk.cop == 32) rc = launch_conv<32, 32, TC_CONV2_DS>(h, kConvNames[1][index], tmMid, tmIn, p, st);
+    else rc = launch_conv<64, 64, TC_CONV2_DS>(h, kConvNames[1][index], tmMid, tmIn, p, st);
   }
   return rc;
 }

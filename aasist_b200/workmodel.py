@@ -27,6 +27,10 @@ def stage_macs(name: str, length: int = 64600):
 def kernel_flops(name: str, kernel: str, batch: int, length: int = 64600) -> float:
     """Algorithmic FLOPs per forward of all launches reported under `kernel`."""
     m = stage_macs(name, length)
+    if kernel.startswith("enc") and "." in kernel:          # "enc{i}.conv1[_tc]" / "enc{i}.conv2[_tc]"
+        blk, conv = kernel.split(".")[0], kernel.split(".")[1]
+        macs = m[f"{blk}.conv1"] if conv.startswith("conv1") else m[f"{blk}.conv2"] + m[f"{blk}.ds"]
+        return 2.0 * macs * batch
     if kernel.startswith("sinc_frontend"):
         macs = m["sinc"]
     elif kernel.startswith("conv1") and "[1->C]" in kernel:
