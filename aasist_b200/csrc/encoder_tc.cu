@@ -45,6 +45,8 @@ struct ConvTcParams {
   const __half* idn;       // CONV2_ID: block input, [B][23][3][J][2*COP]
   const float* z;          // CONV2_Z: block-0 input (B,23,W_in) fp32
   const float* wd;         // CONV2_Z: conv_downsample weights [3][COP] fp32
+  const float* w1;         // CONV2_Z: block-0 conv1 weights (bn2 folded) [6][32] fp32
+  const float* b1;         // CONV2_Z: block-0 conv1 bias (bn2 folded) [32]
   const uint8_t* wimg;     // pre-swizzled weight image (shared-memory layout)
   int wimg_bytes;
 };
@@ -67,18 +69,29 @@ struct TcState {
   void* encode_fn = nullptr;  // cuTensorMapEncodeTiled
 };
 
+__device__ __forceinline__ float ex2_approx(float x) {   // one MUFU.EX2, flush-to-zero, no range branches
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float selu_fast(float v) {
   // scale*max(v,0) + min(0, scale*alpha*(2^(v*log2e) - 1)); the negative branch goes through
   // MUFU.EX2: |abs error| <= ~2.5e-7, the same order as the fp16-pair representation error
-  const float e = exp2f(v * 1.4426950408889634f);
+  const float e = ex2_approx(v * 1.4426950408889634f);
   const float n = fminf(fmaf(e, kSeluScale * kSeluAlpha, -(kSeluScale * kSeluAlpha)), 0.f);
   return fmaf(fmaxf(v, 0.f), kSeluScale, n);
 }
 
-// (a,b) fp32 -> packed hi half2 and lo half2 (a ~= hi+lo to 2^-22), saturating at the fp16 range
+// (a,b) fp32 -> packed hi half2 and lo half2 (a ~= hi+lo to 2^-22), saturating at the fp16 range.
+// LOWER_BOUNDED: the values are SELU outputs (>= -1.76), only the upper clamp is needed.
+template <bool LOWER_BOUNDED = false>
 __device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  a = fminf(fmaxf(a, -65504.f), 65504.f);
-  b = fminf(fmaxf(b, -65504.f), 65504.f);
+  a = fminf(a, 65504.f);
+  b = fminf(b, 65504.f);
+  if (!LOWER_BOUNDED) {
+    a = fmaxf(a, -65504.f);
+    b = fmaxf(b, -65504.f);
+  }
   const __half2 h = __floats2half2_rn(a, b);
   const float2 f = __half22float2(h);
   const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
@@ -86,10 +99,11 @@ __device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 // store 16 fp32 channels as hi (32 B) and lo (32 B) fp16 vectors
+template <bool LOWER_BOUNDED = false>
 __device__ __forceinline__ void store_pair16(__half* hi_dst, __half* lo_dst, const float (&v)[16]) {
   uint32_t hw[8], lw[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) split_pack2(v[2 * i], v[2 * i + 1], hw[i], lw[i]);
+  for (int i = 0; i < 8; ++i) split_pack2<LOWER_BOUNDED>(v[2 * i], v[2 * i + 1], hw[i], lw[i]);
   uint4* hd = reinterpret_cast<uint4*>(hi_dst);
   uint4* ld = reinterpret_cast<uint4*>(lo_dst);
   hd[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
@@ -135,10 +149,31 @@ __device__ __forceinline__ void add_pair16(const Pair16& p, float (&v)[16]) {
 }
 
 // ------------------------------------------------------------------------------------------
-// implicit-GEMM (2,3)/(1,3) convolution on tcgen05
+// implicit-GEMM (2,3)/(1,3) convolution on tcgen05, strip-mined
+//
+// Work item = one (utterance, 128-column strip); the CTA walks the input rows of the strip and
+// every input tile (row r, phase phi) is brought into shared memory ONCE: it feeds the output
+// row it is the upper tap of (dh=0) and the output row it is the lower tap of (dh=1).
+// Two output rows are therefore in flight, one per TMEM accumulator buffer.  With >= 6 ring
+// slots the three phase tiles of a row stay resident and the MMAs run in two passes (dh=1 for
+// all phases -> completes an output row and hands it to the epilogue; then dh=0 -> starts the
+// next one), which gives the epilogue half a row of slack to drain the buffer being recycled.
+//
+// MODE TC_CONV2_Z (encoder block 0) has no TMA at all: its A operand v = selu(bn2(conv1(z)))
+// is COMPUTED by 8 producer warps from the fp32 front-end output z (1 input channel, K = 6:
+// not GEMM-shaped) and written as swizzled fp16 hi/lo tiles straight into the ring, so the
+// 66 MB/utterance intermediate never touches HBM.
 // ------------------------------------------------------------------------------------------
+constexpr int kProdWarps = 8;
+constexpr int kZW = 3 * (kTileJ + 2) + 2;     // z columns a strip needs: 3*130 positions + 1 halo each side
+
+template <int MODE>
+struct ConvCfg {
+  static constexpr int kThreads = kTcThreads + (MODE == TC_CONV2_Z ? 32 * kProdWarps : 0);
+};
+
 template <int CPI, int COP, int MODE>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(ConvCfg<MODE>::kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmS,
                const ConvTcParams p) {
   constexpr int SLABS = CPI / 32;                    // 128-byte-wide K slabs per input tile
@@ -148,9 +183,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr int SIDE_TAP_BYTES = COP * 128;          // side input is 32 channels wide (1 slab)
   constexpr int TMEM_COLS = (6 * COP <= 256) ? 256 : 512;
   constexpr uint32_t IDESC = umma_idesc_f16(128, COP);
-  constexpr int N_MAIN = 6;
-  constexpr int N_SIDE = (MODE == TC_CONV2_DS) ? 3 : 0;
+  constexpr bool FUSED = MODE == TC_CONV2_Z;
+  constexpr bool HAS_SIDE = MODE == TC_CONV2_DS;
   constexpr int NCH = COP / 32;                      // 16-column chunks per epilogue warp (it owns COP/2 columns)
+  constexpr int R_IN = (MODE == TC_CONV1) ? 23 : 24; // input rows walked per strip
+  constexpr int NTHREADS = ConvCfg<MODE>::kThreads;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -162,17 +199,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull = bars + 2 * kMaxSlots;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* s_f32 = reinterpret_cast<float*>(bars + 2 * kMaxSlots + 6);   // FUSED: wd[3][32] then z strip
+  float* s_wd = s_f32;
+  float* s_z = s_f32 + 96;                                             // [23][kZW]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tiles = p.B * p.H_out * p.n_jt;
+  const int n_strips = p.B * p.n_jt;
+  const bool two_pass = p.n_slots >= 6;
 
   // weights: global image -> shared (generic proxy), then make visible to the async proxy
-  for (int i = threadIdx.x; i < p.wimg_bytes / 16; i += kTcThreads)
+  for (int i = threadIdx.x; i < p.wimg_bytes / 16; i += NTHREADS)
     reinterpret_cast<uint4*>(s_w)[i] = __ldg(reinterpret_cast<const uint4*>(p.wimg) + i);
+  if (FUSED)
+    for (int i = threadIdx.x; i < 96; i += NTHREADS) s_wd[i] = __ldg(p.wd + i);
   fence_proxy_async_smem();
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.n_slots; ++i) {
-      mbar_init(&full[i], 1);
+      mbar_init(&full[i], FUSED ? kProdWarps : 1);
       mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -180,8 +223,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&tempty[i], kEpiWarps);   // one arrival per epilogue warp
     }
     fence_barrier_init();
-    prefetch_tensormap(&tmA);
-    if (N_SIDE) prefetch_tensormap(&tmS);
+    if (!FUSED) prefetch_tensormap(&tmA);
+    if (HAS_SIDE) prefetch_tensormap(&tmS);
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_ptr);
   tc_fence_before_sync();
@@ -191,28 +234,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
-    if (lane == 0) {
+    if (!FUSED && lane == 0) {
       int slot = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int h = t % p.H_out, jt = (t / p.H_out) % p.n_jt, b = t / (p.H_out * p.n_jt);
+      for (int t = blockIdx.x; t < n_strips; t += gridDim.x) {
+        const int jt = t % p.n_jt, b = t / p.n_jt;
         const int j0 = jt * kTileJ - 1;
-        for (int it = 0; it < N_MAIN + N_SIDE; ++it) {
-          mbar_wait(&empty[slot], phase ^ 1);
-          uint8_t* dst = s_ring + (size_t)slot * SLOT_BYTES;
-          if (it < N_MAIN) {
-            const int dh = it / 3, phi = it % 3;
-            const int row = (MODE == TC_CONV1) ? h + dh - 1 : h + dh;   // TMA zero-fills row -1 / 23
+        for (int r = 0; r < R_IN; ++r) {
+          for (int phi = 0; phi < 3; ++phi) {
+            mbar_wait(&empty[slot], phase ^ 1);
+            uint8_t* dst = s_ring + (size_t)slot * SLOT_BYTES;
             mbar_arrive_expect_tx(&full[slot], SLABS * kBoxRows * 128);
 #pragma unroll
             for (int sl = 0; sl < SLABS; ++sl)
-              tma_load_5d(dst + sl * kSlabBytes, &tmA, &full[slot], sl * 64, j0, phi, row, b);
-          } else {
-            const int phi = it - N_MAIN;
-            mbar_arrive_expect_tx(&full[slot], kBoxRows * 128);
-            tma_load_5d(dst, &tmS, &full[slot], 0, j0, phi, h, b);
+              tma_load_5d(dst + sl * kSlabBytes, &tmA, &full[slot], sl * 64, j0, phi, r, b);
+            if (++slot == p.n_slots) { slot = 0; phase ^= 1; }
           }
-          if (++slot == p.n_slots) { slot = 0; phase ^= 1; }
+          if (HAS_SIDE && r < 23) {   // conv_downsample input: block input row h = r (output row r)
+            for (int phi = 0; phi < 3; ++phi) {
+              mbar_wait(&empty[slot], phase ^ 1);
+              mbar_arrive_expect_tx(&full[slot], kBoxRows * 128);
+              tma_load_5d(s_ring + (size_t)slot * SLOT_BYTES, &tmS, &full[slot], 0, j0, phi, r, b);
+              if (++slot == p.n_slots) { slot = 0; phase ^= 1; }
+            }
+          }
         }
       }
     }
@@ -221,65 +266,143 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // the whole warp walks the (warp-uniform) schedule; one elected lane issues tcgen05 ops
     int slot = 0;
     uint32_t phase = 0;
-    int tcount = 0;
+    int nstart = 0;                       // output rows started so far (accumulator buffer = nstart & 1)
     const uint32_t w_base = smem_u32(s_w);
+    const uint32_t ring_base = smem_u32(s_ring);
     const bool leader = elect_one();
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
-      const int buf = tcount & 1;
-      mbar_wait(&tempty[buf], ((tcount >> 1) & 1) ^ 1);
-      tc_fence_after_sync();
-      uint32_t started = 0;   // bit s: accumulator s already holds a partial sum
-      for (int it = 0; it < N_MAIN + N_SIDE; ++it) {
-        mbar_wait(&full[slot], phase);
-        tc_fence_after_sync();
-        const uint32_t a_slot = smem_u32(s_ring) + (uint32_t)slot * SLOT_BYTES;
-        const bool side = it >= N_MAIN;
-        const int dh = side ? 0 : it / 3, phi = side ? it - N_MAIN : it % 3;
-        if (leader) {
+
+    // all MMAs of one input tile (phase phi) for tap row dh into accumulator buffer `buf`
+    auto issue_group = [&](int slot_i, int dh, int phi, int buf, bool fresh, bool side) {
+      const uint32_t a_slot = ring_base + (uint32_t)slot_i * SLOT_BYTES;
 #pragma unroll
-          for (int s = 0; s < 3; ++s) {
-            const int d = (phi - s + 3) % 3;              // input phase phi serves pool phase s via tap dw
-            const int dw = d == 0 ? 1 : (d == 1 ? 2 : 0);
-            const int pp = s + dw - 1;                    // offset of the tap in units of phase steps
-            const int shift = pp < 0 ? -1 : (pp > 2 ? 1 : 0);
-            const uint32_t a_row = a_slot + (uint32_t)(1 + shift) * 128;
-            const uint32_t d_tmem = tmem_base + (uint32_t)((buf * 3 + s) * COP);
-            if (!side) {
-              const uint32_t wt = w_base + (uint32_t)((dh * 3 + dw) * TAP_BYTES);
-              const uint64_t a_hi = umma_desc_sw128(a_row);
-              const uint64_t a_lo = umma_desc_sw128((SLABS == 1) ? a_row + 64 : a_row + kSlabBytes);
-              const uint64_t w_hi = umma_desc_sw128(wt);
-              const uint64_t w_lo = umma_desc_sw128((SLABS == 1) ? wt + 64 : wt + COP * 128);
+      for (int s = 0; s < 3; ++s) {
+        const int d = (phi - s + 3) % 3;              // input phase phi serves pool phase s via tap dw
+        const int dw = d == 0 ? 1 : (d == 1 ? 2 : 0);
+        const int pp = s + dw - 1;                    // offset of the tap in units of phase steps
+        const int shift = pp < 0 ? -1 : (pp > 2 ? 1 : 0);
+        const uint32_t a_row = a_slot + (uint32_t)(1 + shift) * 128;
+        const uint32_t d_tmem = tmem_base + (uint32_t)((buf * 3 + s) * COP);
+        if (!side) {
+          const uint32_t wt = w_base + (uint32_t)((dh * 3 + dw) * TAP_BYTES);
+          const uint64_t a_hi = umma_desc_sw128(a_row);
+          const uint64_t a_lo = umma_desc_sw128((SLABS == 1) ? a_row + 64 : a_row + kSlabBytes);
+          const uint64_t w_hi = umma_desc_sw128(wt);
+          const uint64_t w_lo = umma_desc_sw128((SLABS == 1) ? wt + 64 : wt + COP * 128);
 #pragma unroll
-              for (int kc = 0; kc < KC; ++kc) {           // +32 B per K chunk == +2 in the descriptor
-                umma_f16(d_tmem, a_hi + 2 * kc, w_hi + 2 * kc, IDESC, (kc > 0) | ((started >> s) & 1));
-                if (!(p.dbg & 1)) {
-                  umma_f16(d_tmem, a_lo + 2 * kc, w_hi + 2 * kc, IDESC, 1);
-                  umma_f16(d_tmem, a_hi + 2 * kc, w_lo + 2 * kc, IDESC, 1);
-                }
-              }
-            } else {
-              const uint32_t wt = w_base + (uint32_t)(6 * TAP_BYTES + dw * SIDE_TAP_BYTES);
-              const uint64_t a_hi = umma_desc_sw128(a_row), a_lo = umma_desc_sw128(a_row + 64);
-              const uint64_t w_hi = umma_desc_sw128(wt), w_lo = umma_desc_sw128(wt + 64);
-#pragma unroll
-              for (int kc = 0; kc < 2; ++kc) {
-                umma_f16(d_tmem, a_hi + 2 * kc, w_hi + 2 * kc, IDESC, 1);
-                umma_f16(d_tmem, a_lo + 2 * kc, w_hi + 2 * kc, IDESC, 1);
-                umma_f16(d_tmem, a_hi + 2 * kc, w_lo + 2 * kc, IDESC, 1);
-              }
+          for (int kc = 0; kc < KC; ++kc) {           // +32 B per K chunk == +2 in the descriptor
+            umma_f16(d_tmem, a_hi + 2 * kc, w_hi + 2 * kc, IDESC, (kc > 0 || !fresh) ? 1u : 0u);
+            if (!(p.dbg & 1)) {
+              umma_f16(d_tmem, a_lo + 2 * kc, w_hi + 2 * kc, IDESC, 1);
+              umma_f16(d_tmem, a_hi + 2 * kc, w_lo + 2 * kc, IDESC, 1);
             }
           }
-          umma_commit(&empty[slot]);                      // slot reusable once these MMAs retire
+        } else {
+          const uint32_t wt = w_base + (uint32_t)(6 * TAP_BYTES + dw * SIDE_TAP_BYTES);
+          const uint64_t a_hi = umma_desc_sw128(a_row), a_lo = umma_desc_sw128(a_row + 64);
+          const uint64_t w_hi = umma_desc_sw128(wt), w_lo = umma_desc_sw128(wt + 64);
+#pragma unroll
+          for (int kc = 0; kc < 2; ++kc) {
+            umma_f16(d_tmem, a_hi + 2 * kc, w_hi + 2 * kc, IDESC, 1);
+            umma_f16(d_tmem, a_lo + 2 * kc, w_hi + 2 * kc, IDESC, 1);
+            umma_f16(d_tmem, a_hi + 2 * kc, w_lo + 2 * kc, IDESC, 1);
+          }
         }
-        started = 7;
-        __syncwarp();
-        if (++slot == p.n_slots) { slot = 0; phase ^= 1; }
       }
-      if (leader) umma_commit(&tfull[buf]);               // accumulators of this tile complete
-      __syncwarp();
+    };
+    auto advance = [&](int& sl, uint32_t& ph) {
+      if (++sl == p.n_slots) { sl = 0; ph ^= 1; }
+    };
+    auto begin_row = [&]() -> int {       // claim the next accumulator buffer (waits for its drain)
+      const int buf = nstart & 1;
+      mbar_wait(&tempty[buf], ((nstart >> 1) & 1) ^ 1);
+      tc_fence_after_sync();
+      ++nstart;
+      return buf;
+    };
+
+    for (int t = blockIdx.x; t < n_strips; t += gridDim.x) {
+      int buf_open = 0;                   // buffer of the output row that is currently half done
+      for (int r = 0; r < R_IN; ++r) {
+        // input row r: dh=1 completes output row o1, dh=0 starts output row o0
+        const bool has_o1 = (MODE == TC_CONV1) ? true : (r >= 1);
+        const bool has_o0 = (MODE == TC_CONV1) ? true : (r <= 22);
+        const bool o1_fresh = (MODE == TC_CONV1) && r == 0;          // conv1 row 0 has no dh=0 tap (zero pad)
+        const bool o0_closes = (MODE == TC_CONV1) && r == R_IN - 1;  // conv1 row 23 has no dh=1 tap
+        int sl[3];
+        uint32_t ph[3];
+        {
+          int s2 = slot;
+          uint32_t p2 = phase;
+          for (int i = 0; i < 3; ++i) { sl[i] = s2; ph[i] = p2; advance(s2, p2); }
+        }
+        if (two_pass) {
+          if (o1_fresh) buf_open = begin_row();
+          for (int phi = 0; phi < 3; ++phi) {
+            mbar_wait(&full[sl[phi]], ph[phi]);
+            tc_fence_after_sync();
+            if (has_o1 && leader) issue_group(sl[phi], 1, phi, buf_open, o1_fresh && phi == 0, false);
+            __syncwarp();
+          }
+          if (has_o1) {
+            if (leader) umma_commit(&tfull[buf_open]);               // output row o1 complete
+            __syncwarp();
+          }
+          if (has_o0) {
+            buf_open = begin_row();
+            for (int phi = 0; phi < 3; ++phi) {
+              if (leader) {
+                issue_group(sl[phi], 0, phi, buf_open, phi == 0, false);
+                umma_commit(&empty[sl[phi]]);
+              }
+              __syncwarp();
+            }
+          } else {
+            for (int phi = 0; phi < 3; ++phi) {
+              if (leader) umma_commit(&empty[sl[phi]]);
+              __syncwarp();
+            }
+          }
+        } else {
+          int buf_new = -1;
+          if (o1_fresh) buf_open = begin_row();
+          for (int phi = 0; phi < 3; ++phi) {
+            mbar_wait(&full[sl[phi]], ph[phi]);
+            tc_fence_after_sync();
+            if (has_o1 && leader) issue_group(sl[phi], 1, phi, buf_open, o1_fresh && phi == 0, false);
+            __syncwarp();
+            if (has_o0) {
+              if (phi == 0) buf_new = begin_row();
+              if (leader) issue_group(sl[phi], 0, phi, buf_new, phi == 0, false);
+            }
+            if (leader) umma_commit(&empty[sl[phi]]);
+            __syncwarp();
+          }
+          if (has_o1) {
+            if (leader) umma_commit(&tfull[buf_open]);
+            __syncwarp();
+          }
+          if (has_o0) buf_open = buf_new;
+        }
+        for (int i = 0; i < 3; ++i) advance(slot, phase);
+        if (HAS_SIDE && has_o0) {
+          for (int phi = 0; phi < 3; ++phi) {
+            mbar_wait(&full[slot], phase);
+            tc_fence_after_sync();
+            if (leader) {
+              issue_group(slot, 0, phi, buf_open, false, true);
+              umma_commit(&empty[slot]);
+            }
+            __syncwarp();
+            advance(slot, phase);
+          }
+        }
+        if (has_o0 && o0_closes) {
+          if (leader) umma_commit(&tfull[buf_open]);
+          __syncwarp();
+        }
+      }
     }
-  } else {
+  } else if (warp < 2 + kEpiWarps) {
     // =============================== epilogue (warps 2..9) ========================
     // warp -> (TMEM lane quadrant, column half): thread = one pooled column j, COP/2 channels
     const int quad = warp & 3;
@@ -291,125 +414,201 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int c = 0; c < NCH; ++c)
 #pragma unroll
       for (int i = 0; i < 16; ++i) bias[c][i] = __ldg(p.bias + col0 + c * 16 + i);
-    float wdr[(MODE == TC_CONV2_Z) ? 3 : 1][NCH][16];
-    if (MODE == TC_CONV2_Z) {
-#pragma unroll
-      for (int t = 0; t < 3; ++t)
-#pragma unroll
-        for (int c = 0; c < NCH; ++c)
-#pragma unroll
-          for (int i = 0; i < 16; ++i) wdr[t][c][i] = __ldg(p.wd + t * COP + col0 + c * 16 + i);
-    }
     int tcount = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
-      const int h = t % p.H_out, jt = (t / p.H_out) % p.n_jt, b = t / (p.H_out * p.n_jt);
-      const int buf = tcount & 1;
+    for (int t = blockIdx.x; t < n_strips; t += gridDim.x) {
+      const int jt = t % p.n_jt, b = t / p.n_jt;
       const int j = jt * kTileJ + r;
-      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 3 * COP + col0);
-      if (MODE == TC_CONV1) {
-        mbar_wait(&tfull[buf], (tcount >> 1) & 1);
-        tc_fence_after_sync();
-        // out[b][h][s][j][:] = selu(acc + b1), zero beyond the valid width
-        uint32_t acc[3][NCH][16];
-#pragma unroll
-        for (int s = 0; s < 3; ++s)
-#pragma unroll
-          for (int c = 0; c < NCH; ++c) tmem_ld16_async(t_row + (uint32_t)(s * COP + c * 16), acc[s][c]);
-#pragma unroll
-        for (int s = 0; s < 3; ++s)
-#pragma unroll
-          for (int c = 0; c < NCH; ++c) tmem_ld_wait16(acc[s][c]);
-        // the accumulators are in registers: release the TMEM buffer before the math / stores
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[buf]);
-        if (p.dbg & 2) continue;
-#pragma unroll
-        for (int s = 0; s < 3; ++s) {
-          const bool valid = 3 * j + s < p.W_in;
-#pragma unroll
-          for (int c = 0; c < NCH; ++c) {
-            float v[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              v[i] = valid ? selu_fast(__uint_as_float(acc[s][c][i]) + bias[c][i]) : 0.f;
-            if (j < p.J) {
-              __half* o = p.out + ((((size_t)b * 24 + h) * 3 + s) * p.J + j) * (2 * COP) + col0 + c * 16;
-              store_pair16(o, o + COP, v);
-            }
-          }
-        }
-      } else {
-        // operands that do not depend on the accumulators are fetched before waiting for them
-        Pair16 idn[(MODE == TC_CONV2_ID) ? 3 : 1][NCH];
-        float zq[5];
-        if (MODE == TC_CONV2_ID) {
+      for (int h = 0; h < p.H_out; ++h, ++tcount) {
+        const int buf = tcount & 1;
+        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 3 * COP + col0);
+        if (MODE == TC_CONV1) {
+          mbar_wait(&tfull[buf], (tcount >> 1) & 1);
+          tc_fence_after_sync();
+          // out[b][h][s][j][:] = selu(acc + b1), zero beyond the valid width
+          uint32_t acc[3][NCH][16];
 #pragma unroll
           for (int s = 0; s < 3; ++s)
 #pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-              if (j < p.J) {
-                const __half* x = p.idn + ((((size_t)b * 23 + h) * 3 + s) * p.J + j) * (2 * COP) + col0 + c * 16;
-                idn[s][c] = load_pair16(x, x + COP);
-              } else {
-                idn[s][c] = zero_pair16();
-              }
-            }
-        } else if (MODE == TC_CONV2_Z) {
-          const float* zr = p.z + ((size_t)b * 23 + h) * p.W_in;
+            for (int c = 0; c < NCH; ++c) tmem_ld16_async(t_row + (uint32_t)(s * COP + c * 16), acc[s][c]);
 #pragma unroll
-          for (int i = 0; i < 5; ++i) {
-            const int w = 3 * j - 1 + i;
-            zq[i] = (w >= 0 && w < p.W_in) ? __ldg(zr + w) : 0.f;
-          }
-        }
-        mbar_wait(&tfull[buf], (tcount >> 1) & 1);
-        tc_fence_after_sync();
-        const bool valid = j < p.Wo;
-        uint32_t acc[3][NCH][16];
+          for (int s = 0; s < 3; ++s)
 #pragma unroll
-        for (int s = 0; s < 3; ++s)
-#pragma unroll
-          for (int c = 0; c < NCH; ++c) tmem_ld16_async(t_row + (uint32_t)(s * COP + c * 16), acc[s][c]);
-#pragma unroll
-        for (int s = 0; s < 3; ++s)
-#pragma unroll
-          for (int c = 0; c < NCH; ++c) tmem_ld_wait16(acc[s][c]);
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[buf]);
-        if (p.dbg & 2) continue;
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          float m[16];
+            for (int c = 0; c < NCH; ++c) tmem_ld_wait16(acc[s][c]);
+          // the accumulators are in registers: release the TMEM buffer before the math / stores
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[buf]);
+          if (p.dbg & 2) continue;
 #pragma unroll
           for (int s = 0; s < 3; ++s) {
-            float v[16];
+            const bool valid = 3 * j + s < p.W_in;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[s][c][i]);
-            if (MODE == TC_CONV2_ID) {
-              add_pair16(idn[s][c], v);
-            } else if (MODE == TC_CONV2_Z) {
+            for (int c = 0; c < NCH; ++c) {
+              float v[16];
 #pragma unroll
               for (int i = 0; i < 16; ++i)
-                v[i] += wdr[0][c][i] * zq[s] + wdr[1][c][i] * zq[s + 1] + wdr[2][c][i] * zq[s + 2];
+                v[i] = valid ? selu_fast(__uint_as_float(acc[s][c][i]) + bias[c][i]) : 0.f;
+              if (j < p.J) {
+                __half* o = p.out + ((((size_t)b * 24 + h) * 3 + s) * p.J + j) * (2 * COP) + col0 + c * 16;
+                store_pair16<true>(o, o + COP, v);
+              }
+            }
+          }
+        } else {
+          // operands that do not depend on the accumulators are fetched before waiting for them
+          Pair16 idn[(MODE == TC_CONV2_ID) ? 3 : 1][NCH];
+          float zq[5];
+          if (MODE == TC_CONV2_ID) {
+#pragma unroll
+            for (int s = 0; s < 3; ++s)
+#pragma unroll
+              for (int c = 0; c < NCH; ++c) {
+                if (j < p.J) {
+                  const __half* x = p.idn + ((((size_t)b * 23 + h) * 3 + s) * p.J + j) * (2 * COP) + col0 + c * 16;
+                  idn[s][c] = load_pair16(x, x + COP);
+                } else {
+                  idn[s][c] = zero_pair16();
+                }
+              }
+          } else if (MODE == TC_CONV2_Z) {
+            const float* zr = p.z + ((size_t)b * 23 + h) * p.W_in;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+              const int w = 3 * j - 1 + i;
+              zq[i] = (w >= 0 && w < p.W_in) ? __ldg(zr + w) : 0.f;
+            }
+          }
+          mbar_wait(&tfull[buf], (tcount >> 1) & 1);
+          tc_fence_after_sync();
+          const bool valid = j < p.Wo;
+          uint32_t acc[3][NCH][16];
+#pragma unroll
+          for (int s = 0; s < 3; ++s)
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) tmem_ld16_async(t_row + (uint32_t)(s * COP + c * 16), acc[s][c]);
+#pragma unroll
+          for (int s = 0; s < 3; ++s)
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) tmem_ld_wait16(acc[s][c]);
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[buf]);
+          if (p.dbg & 2) continue;
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            float m[16];
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+              float v[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[s][c][i]);
+              if (MODE == TC_CONV2_ID) {
+                add_pair16(idn[s][c], v);
+              } else if (MODE == TC_CONV2_Z) {
+                // conv_downsample (1 -> COP channels, k(1,3)) on CUDA cores; weights broadcast from smem
+#pragma unroll
+                for (int i4 = 0; i4 < 4; ++i4) {
+                  const float4 w0 = *reinterpret_cast<const float4*>(s_wd + col0 + c * 16 + 4 * i4);
+                  const float4 w1 = *reinterpret_cast<const float4*>(s_wd + 32 + col0 + c * 16 + 4 * i4);
+                  const float4 w2 = *reinterpret_cast<const float4*>(s_wd + 64 + col0 + c * 16 + 4 * i4);
+                  v[4 * i4 + 0] += w0.x * zq[s] + w1.x * zq[s + 1] + w2.x * zq[s + 2];
+                  v[4 * i4 + 1] += w0.y * zq[s] + w1.y * zq[s + 1] + w2.y * zq[s + 2];
+                  v[4 * i4 + 2] += w0.z * zq[s] + w1.z * zq[s + 1] + w2.z * zq[s + 2];
+                  v[4 * i4 + 3] += w0.w * zq[s] + w1.w * zq[s + 1] + w2.w * zq[s + 2];
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 16; ++i) m[i] = s == 0 ? v[i] : fmaxf(m[i], v[i]);
             }
 #pragma unroll
-            for (int i = 0; i < 16; ++i) m[i] = s == 0 ? v[i] : fmaxf(m[i], v[i]);
-          }
+            for (int i = 0; i < 16; ++i) m[i] = valid ? m[i] + bias[c][i] : 0.f;
+            if (p.out_f32) {
+              if (valid)
 #pragma unroll
-          for (int i = 0; i < 16; ++i) m[i] = valid ? m[i] + bias[c][i] : 0.f;
-          if (p.out_f32) {
-            if (valid)
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const int ch = col0 + c * 16 + i;
-                if (ch < p.Co) p.out_f32[(((size_t)b * p.Co + ch) * 23 + h) * p.Wo + j] = m[i];
-              }
-          } else if (j / 3 < p.Jn) {
-            __half* o = p.out + ((((size_t)b * 23 + h) * 3 + (j % 3)) * p.Jn + j / 3) * (2 * COP) + col0 + c * 16;
-            store_pair16(o, o + COP, m);
+                for (int i = 0; i < 16; ++i) {
+                  const int ch = col0 + c * 16 + i;
+                  if (ch < p.Co) p.out_f32[(((size_t)b * p.Co + ch) * 23 + h) * p.Wo + j] = m[i];
+                }
+            } else if (j / 3 < p.Jn) {
+              __half* o = p.out + ((((size_t)b * 23 + h) * 3 + (j % 3)) * p.Jn + j / 3) * (2 * COP) + col0 + c * 16;
+              store_pair16(o, o + COP, m);
+            }
           }
+        }
+      }
+    }
+  } else if (FUSED) {
+    // ============ operand producers (warps 10..17): v = selu(bn2(conv1(z))) -> swizzled ring tiles ============
+    // thread (row jj in an 8-row group, channel octet cg): lane = cg*8 + (jj & 7) so that a
+    // quarter-warp writes eight different rows of the same 16-byte chunk column -> the XOR
+    // swizzle spreads them over all banks.
+    const int pw = warp - (2 + kEpiWarps);
+    const int ptid = threadIdx.x - 32 * (2 + kEpiWarps);
+    const int cg = lane >> 3, rr = lane & 7;
+    float w1[6][8], b1[8];
+#pragma unroll
+    for (int tp = 0; tp < 6; ++tp)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) w1[tp][i] = __ldg(p.w1 + tp * 32 + cg * 8 + i);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) b1[i] = __ldg(p.b1 + cg * 8 + i);
+    int slot = 0;
+    uint32_t phase = 0;
+    uint32_t gseq = 0;                    // running 8-row-group counter: balances groups over the warps
+    for (int t = blockIdx.x; t < n_strips; t += gridDim.x) {
+      const int jt = t % p.n_jt, b = t / p.n_jt;
+      const int jstart = jt * kTileJ - 1;
+      const int wz0 = 3 * jstart - 1;     // global column of s_z[.][0]
+      // producers-only barrier: everyone is done reading the previous strip's z
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kProdWarps) : "memory");
+      for (int i = ptid; i < 23 * kZW; i += 32 * kProdWarps) {
+        const int row = i / kZW, col = i % kZW, w = wz0 + col;
+        s_z[i] = (w >= 0 && w < p.W_in) ? __ldg(p.z + ((size_t)b * 23 + row) * p.W_in + w) : 0.f;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kProdWarps) : "memory");
+      for (int r = 0; r < 24; ++r) {
+        const float* z_up = s_z + (r - 1) * kZW;   // conv1 tap dh=0 reads z row r-1 (zero pad outside 0..22)
+        const float* z_dn = s_z + r * kZW;         // tap dh=1 reads z row r
+        const bool up_ok = r >= 1, dn_ok = r <= 22;
+        for (int phi = 0; phi < 3; ++phi) {
+          mbar_wait(&empty[slot], phase ^ 1);
+          uint8_t* dst = s_ring + (size_t)slot * SLOT_BYTES;
+          // 17 eight-row groups per tile, dealt round-robin (running offset) to the producer warps
+          const int g_first = (int)((pw + kProdWarps - (gseq % kProdWarps)) % kProdWarps);
+          gseq += 17;
+          for (int g = g_first; g < 17; g += kProdWarps) {
+            const int jj = g * 8 + rr;             // tile row; 130..135 are never read by the MMAs
+            const int pos = 3 * (jstart + jj) + phi;
+            const int zi = 3 * jj + phi;           // s_z column of position pos-1
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = b1[i];
+            float a[6];
+#pragma unroll
+            for (int dw = 0; dw < 3; ++dw) {
+              const int zc = min(zi + dw, kZW - 1);
+              a[dw] = up_ok ? z_up[zc] : 0.f;
+              a[3 + dw] = dn_ok ? z_dn[zc] : 0.f;
+            }
+#pragma unroll
+            for (int tp = 0; tp < 6; ++tp)
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = fmaf(a[tp], w1[tp][i], v[i]);
+            const bool valid = pos >= 0 && pos < p.W_in;   // conv2 zero-pads v itself
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float x0 = valid ? selu_fast(v[2 * i]) : 0.f, x1 = valid ? selu_fast(v[2 * i + 1]) : 0.f;
+              split_pack2<true>(x0, x1, hw[i], lw[i]);
+            }
+            uint8_t* row = dst + jj * 128;
+            *reinterpret_cast<uint4*>(row + ((cg ^ rr) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(row + (((4 + cg) ^ rr) << 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
+          fence_proxy_async_smem();          // generic-proxy stores -> visible to tcgen05 operand fetch
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full[slot]);
+          if (++slot == p.n_slots) { slot = 0; phase ^= 1; }
         }
       }
     }
@@ -420,62 +619,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after_sync();
     tmem_dealloc<TMEM_COLS>(tmem_base);
   }
-}
-
-// ------------------------------------------------------------------------------------------
-// block 0 conv1 (1 -> 32 channels, K = 6): not GEMM-shaped, CUDA cores.
-// z (B,23,W) fp32 -> v [B][24][3][J][64] fp16 pairs, v = selu(bn2(conv1(z)))
-// thread = one position, all 32 channels; weights broadcast from shared memory.
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-block0_conv1_kernel(const float* __restrict__ z, const float* __restrict__ w /*[6][32]*/,
-                    const float* __restrict__ bias /*[32]*/, __half* __restrict__ out, int W, int J) {
-  __shared__ __align__(16) float s_w[6 * 32 + 32];
-  for (int i = threadIdx.x; i < 6 * 32; i += 128) s_w[i] = w[i];
-  if (threadIdx.x < 32) s_w[192 + threadIdx.x] = bias[threadIdx.x];
-  __syncthreads();
-  const int j = blockIdx.x * 128 + threadIdx.x;
-  const int r = blockIdx.y / 3, phi = blockIdx.y % 3;   // output row 0..23
-  const int b = blockIdx.z;
-  if (j >= J) return;
-  const int pos = 3 * j + phi;
-  float v[32];
-  if (pos < W) {
-    float in[2][3];
-#pragma unroll
-    for (int dh = 0; dh < 2; ++dh) {
-      const int row = r + dh - 1;
-#pragma unroll
-      for (int dw = 0; dw < 3; ++dw) {
-        const int ww = pos + dw - 1;
-        in[dh][dw] = (row >= 0 && row < 23 && ww >= 0 && ww < W) ? __ldg(z + ((size_t)b * 23 + row) * W + ww) : 0.f;
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < 32; ++c) v[c] = s_w[192 + c];
-#pragma unroll
-    for (int dh = 0; dh < 2; ++dh)
-#pragma unroll
-      for (int dw = 0; dw < 3; ++dw) {
-        const float a = in[dh][dw];
-        const float4* wp = reinterpret_cast<const float4*>(s_w + (dh * 3 + dw) * 32);
-#pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-          float4 ww = wp[c4];
-          v[4 * c4] = fmaf(a, ww.x, v[4 * c4]);
-          v[4 * c4 + 1] = fmaf(a, ww.y, v[4 * c4 + 1]);
-          v[4 * c4 + 2] = fmaf(a, ww.z, v[4 * c4 + 2]);
-          v[4 * c4 + 3] = fmaf(a, ww.w, v[4 * c4 + 3]);
-        }
-      }
-#pragma unroll
-    for (int c = 0; c < 32; ++c) v[c] = selu_fast(v[c]);
-  } else {
-#pragma unroll
-    for (int c = 0; c < 32; ++c) v[c] = 0.f;
-  }
-  __half* o = out + ((((size_t)b * 24 + r) * 3 + phi) * J + j) * 64;
-  store_pair32(o, o + 32, v);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -726,29 +869,29 @@ template <int CPI, int COP, int MODE>
 static int launch_conv(aasist_handle* h, const char* name, const CUtensorMap& tmA, const CUtensorMap& tmS,
                        ConvTcParams p, cudaStream_t st) {
   constexpr int SLOT = (CPI / 32) * kSlabBytes;
-  const int budget = 227 * 1024 - 1024 /*align*/ - p.wimg_bytes - 256 /*barriers*/;
+  constexpr int EXTRA = (MODE == TC_CONV2_Z) ? (96 + 23 * kZW) * 4 : 0;   // wd + z strip (fused block 0)
+  const int budget = 227 * 1024 - 1024 /*align*/ - p.wimg_bytes - 256 /*barriers*/ - EXTRA;
   int n_slots = std::min(kMaxSlots, budget / SLOT);
   if (n_slots < 2) {
     set_error("conv_tc: not enough shared memory for the input ring (weights %d bytes)", p.wimg_bytes);
     return AASIST_E_INVALID;
   }
-  p.n_slots = n_slots;
   {
-    static int dbg = -1;
+    static int dbg = -1, slots_override = -1;
     if (dbg < 0) { const char* e = getenv("AASIST_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
-    p.dbg = dbg;
-    static int slots_override = -1;
     if (slots_override < 0) { const char* e = getenv("AASIST_TC_SLOTS"); slots_override = e ? atoi(e) : 0; }
-    if (slots_override >= 2 && slots_override <= n_slots) p.n_slots = n_slots = slots_override;
+    p.dbg = dbg;
+    if (slots_override >= 2 && slots_override <= n_slots) n_slots = slots_override;
   }
-  size_t smem = 1024 + (size_t)p.wimg_bytes + (size_t)n_slots * SLOT + 256;
+  p.n_slots = n_slots;
+  size_t smem = 1024 + (size_t)p.wimg_bytes + (size_t)n_slots * SLOT + 256 + EXTRA;
   auto kern = conv_tc_kernel<CPI, COP, MODE>;
   AASIST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int n_tiles = p.B * p.H_out * p.n_jt;
-  int grid = std::min(n_tiles, h->tc->sm_count);
+  const int n_strips = p.B * p.n_jt;
+  const int grid = std::min(n_strips, h->tc->sm_count);
   {
     LaunchSpan span(h, name, st);
-    kern<<<grid, kTcThreads, smem, st>>>(tmA, tmS, p);
+    kern<<<grid, ConvCfg<MODE>::kThreads, smem, st>>>(tmA, tmS, p);
   }
   AASIST_CUDA(cudaGetLastError());
   return 0;
@@ -769,14 +912,11 @@ static int run_block_tc(aasist_handle* h, int enc, int index, const __half* in_p
   int rc;
   CUtensorMap tmIn, tmMid;
   memset(&tmIn, 0, sizeof(tmIn));
-  if ((rc = make_act_tmap(h, &tmMid, mid, blk.cop, J, 24, nb))) return rc;
+  memset(&tmMid, 0, sizeof(tmMid));
+  if (index > 0 && (rc = make_act_tmap(h, &tmMid, mid, blk.cop, J, 24, nb))) return rc;
   if (index > 0 && (rc = make_act_tmap(h, &tmIn, in_pairs, blk.cpi, J, 23, nb))) return rc;
-  // ---- conv1 ----
-  if (index == 0) {
-    dim3 grid((J + 127) / 128, 24 * 3, nb);
-    LaunchSpan span(h, kConvNames[0][0], st);
-    block0_conv1_kernel<<<grid, 128, 0, st>>>(z, blk.w1_f32, blk.c1.bias, mid, W, J);
-  } else {
+  // ---- conv1 (block 0: fused into the conv2 kernel as its operand producer) ----
+  if (index > 0) {
     ConvTcParams p;
     memset(&p, 0, sizeof(p));
     p.B = nb; p.H_out = 24; p.J = J; p.n_jt = (J + kTileJ - 1) / kTileJ; p.W_in = W; p.Co = blk.co;
@@ -795,8 +935,8 @@ static int run_block_tc(aasist_handle* h, int enc, int index, const __half* in_p
   p.n_jt = (std::max(J, std::min(3 * Jn, Wo + 2)) + kTileJ - 1) / kTileJ;
   p.bias = blk.c2.bias; p.out = out_pairs; p.out_f32 = out_f32; p.wimg = blk.c2.wimg; p.wimg_bytes = blk.c2.wimg_bytes;
   if (index == 0) {
-    p.z = z; p.wd = blk.wd_f32;
-    rc = launch_conv<32, 32, TC_CONV2_Z>(h, kConvNames[1][index], tmMid, tmMid, p, st);
+    p.z = z; p.wd = blk.wd_f32; p.w1 = blk.w1_f32; p.b1 = blk.c1.bias;
+    rc = launch_conv<32, 32, TC_CONV2_Z>(h, "enc0.fused_conv1_conv2_tc", tmIn, tmIn, p, st);
   } else if (!blk.downsample) {
     p.idn = in_pairs;
     if (blk.cop == 32) rc = launch_conv<32, 32, TC_CONV2_ID>(h, kConvNames[1][index], tmMid, tmMid, p, st);

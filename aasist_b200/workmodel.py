@@ -29,7 +29,10 @@ def kernel_flops(name: str, kernel: str, batch: int, length: int = 64600) -> flo
     m = stage_macs(name, length)
     if kernel.startswith("enc") and "." in kernel:          # "enc{i}.conv1[_tc]" / "enc{i}.conv2[_tc]"
         blk, conv = kernel.split(".")[0], kernel.split(".")[1]
-        macs = m[f"{blk}.conv1"] if conv.startswith("conv1") else m[f"{blk}.conv2"] + m[f"{blk}.ds"]
+        if conv.startswith("fused"):
+            macs = m[f"{blk}.conv1"] + m[f"{blk}.conv2"] + m[f"{blk}.ds"]
+        else:
+            macs = m[f"{blk}.conv1"] if conv.startswith("conv1") else m[f"{blk}.conv2"] + m[f"{blk}.ds"]
         return 2.0 * macs * batch
     if kernel.startswith("sinc_frontend"):
         macs = m["sinc"]
