@@ -67,6 +67,7 @@ struct TcState {
   BlockTc blocks[2][6];
   int sm_count = 148;
   void* encode_fn = nullptr;  // cuTensorMapEncodeTiled
+  uint8_t* front_bimg = nullptr;  // sinc filter operand image (frontend_tc.cu)
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {   // one MUFU.EX2, flush-to-zero, no range branches
@@ -821,7 +822,7 @@ int tc_finalize(aasist_handle* h) {
       int rc = pack_block_tc(h, p, i, tc->blocks[e][i]);
       if (rc) return rc;
     }
-  return 0;
+  return tc_front_finalize(h, &tc->front_bimg);
 }
 
 void tc_destroy(aasist_handle* h) {
@@ -832,6 +833,7 @@ void tc_destroy(aasist_handle* h) {
       cudaFree(b.c1.wimg); cudaFree(b.c1.bias); cudaFree(b.c2.wimg); cudaFree(b.c2.bias);
       cudaFree(b.w1_f32); cudaFree(b.wd_f32);
     }
+  cudaFree(h->tc->front_bimg);
   delete h->tc;
   h->tc = nullptr;
 }
@@ -965,7 +967,10 @@ int tc_encode(aasist_handle* h, const float* x, int B, int L, float** enc_out, v
   const size_t enc_per = (size_t)C * kSpecNodes * pl.W[6];
   for (int b0 = 0; b0 < B; b0 += nbmax) {
     const int nb = std::min(nbmax, B - b0);
-    int rc = launch_frontend_f32(h, x + (size_t)b0 * L, nb, L, z, st);
+    static int f32_front = -1;   // AASIST_TC_F32_FRONT=1: timing experiments with the CUDA-core sinc stage
+    if (f32_front < 0) { const char* e = getenv("AASIST_TC_F32_FRONT"); f32_front = e ? atoi(e) : 0; }
+    int rc = f32_front ? launch_frontend_f32(h, x + (size_t)b0 * L, nb, L, z, st)
+                       : launch_frontend_tc(h, h->tc->front_bimg, h->tc->sm_count, x + (size_t)b0 * L, nb, L, z, st);
     if (rc) return rc;
     for (int e = 0; e < h->n_encoders; ++e) {
       const __half* in = nullptr;
@@ -982,7 +987,7 @@ int tc_encode(aasist_handle* h, const float* x, int B, int L, float** enc_out, v
 
 int tc_frontend_to_f32(aasist_handle* h, const float* x, int B, int L, float* out, void*, int64_t,
                        cudaStream_t st) {
-  return launch_frontend_f32(h, x, B, L, out, st);   // the sinc stage of this path is still fp32
+  return launch_frontend_tc(h, h->tc->front_bimg, h->tc->sm_count, x, B, L, out, st);
 }
 
 int tc_block_f32io(aasist_handle* h, int enc, int index, const float* in, int B, int W, float* out, void* ws,

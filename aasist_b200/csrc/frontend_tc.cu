@@ -1,0 +1,285 @@
+// Sinc front end on the tensor cores (reference models/AASIST.py:497-503, 829-831):
+// valid 129-tap cross-correlation of the waveform with the 70-filter bank, |.|, 3x3 max-pool
+// (band x time), first_bn, SELU -- one kernel, the (B,70,L-128) conv output never exists.
+//
+// GEMM formulation.  A CTA tile is 128 POOLED time steps ti (384 conv outputs).  The pool phase
+// s = t mod 3 is folded into the filter operand instead of the signal operand:
+//     D[ti][n] = sum_k' A[ti][k'] * H[n][k'],     A[ti][k'] = x[3*(ti0+ti) + k'],  k' < 131 (pad 144)
+//     n = 9*fi + 3*df + s  <->  H[n][k'] = h[3*fi+df][k' - s]   (zero outside 0..128)
+// so ONE Hankel-like A tile (rows overlap with stride 3 samples: TMA cannot express it, producer
+// warps build it in shared memory from a staged fp16 copy of the waveform segment) is multiplied by
+// a resident 208 x 144 filter operand, and the 9 columns of a pooled band fi -- 3 filters x 3
+// phases -- are adjacent, so |.|/max-pool is register-local in the epilogue.  N = 23*9 = 207 -> 208.
+// Operands are fp16 hi/lo pairs (x and h pre-scaled by 2^10, undone exactly in the epilogue),
+// 3 products per K chunk, fp32 accumulation in TMEM (same scheme as encoder_tc.cu).
+//
+// Both operands use the no-swizzle K-major canonical layout (8-row x 16-byte core matrices):
+//   addr(row, kbyte) = chunk*CHUNK + (row/8)*256 + (kbyte/16)*128 + (row%8)*16 + kbyte%16
+// i.e. SBO = 256 B (next 8-row group), LBO = 128 B (second 16-byte K half of a UMMA_K=16 chunk).
+// The A tile is a 9-slot ring indexed by K chunk: the MMA warp releases chunk kc of tile t
+// (tcgen05.commit) and the producers immediately rebuild it for tile t+1.
+#include <algorithm>
+
+#include "ptx.cuh"
+#include "tc.cuh"
+
+namespace aasist {
+
+using namespace ptx;
+
+constexpr int kFtTile = 128;                  // pooled steps per tile (UMMA M)
+constexpr int kFtN = 208;                     // 23 bands x 9 (3 filters x 3 phases), padded to /16
+constexpr int kFtKC = 9;                      // K chunks of 16: 131 taps+phases -> 144
+constexpr int kFtAChunk = kFtTile * 32;       // bytes of one A K-chunk (hi or lo)
+constexpr int kFtBChunk = kFtN * 32;          // bytes of one B K-chunk (hi or lo)
+constexpr int kFtSeg = 3 * kFtTile + 16 * kFtKC;   // staged samples per tile (527 used)
+constexpr int kFtProdWarps = 4;               // 128 producer threads: one per A row
+constexpr int kFtThreads = 64 + 32 * 8 + 32 * kFtProdWarps;
+constexpr int kFtBufCols = 256;               // TMEM column stride between the two accumulators
+constexpr float kFtScale = 1024.f;            // 2^10 on both operands
+
+struct FrontTcParams {
+  const float* x;          // (B, L)
+  float* out;              // (B, 23, Wp)
+  const uint8_t* bimg;     // filter operand image: [hi|lo][kc][208 rows x 32 B], no-swizzle canonical
+  int B, L, Wp, n_tiles_per_utt;
+  float bn_scale, bn_shift;
+};
+
+// no-swizzle K-major descriptor: LBO = 128 B, SBO = 256 B, version 1, layout 0
+__device__ __forceinline__ uint64_t umma_desc_noswz(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) |
+         ((uint64_t)1 << 46);
+}
+
+__device__ __forceinline__ float ft_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ft_selu(float v) {
+  const float e = ft_ex2(v * 1.4426950408889634f);
+  const float n = fminf(fmaf(e, kSeluScale * kSeluAlpha, -(kSeluScale * kSeluAlpha)), 0.f);
+  return fmaf(fmaxf(v, 0.f), kSeluScale, n);
+}
+
+// epilogue of one half of the bands: HALF 0 -> fi 0..11 (columns 0..107), HALF 1 -> fi 12..22
+// (columns 108..206).  Loads are issued at 16-aligned column offsets.
+template <int HALF>
+__device__ __forceinline__ void front_epilogue(uint32_t t_row, const FrontTcParams& p, int b, int ti,
+                                               uint64_t* tempty_bar, int lane) {
+  constexpr int COL0 = HALF == 0 ? 0 : 96;           // first loaded column (16-aligned)
+  constexpr int FI0 = HALF == 0 ? 0 : 12, NFI = HALF == 0 ? 12 : 11;
+  uint32_t acc[7][16];
+#pragma unroll
+  for (int c = 0; c < 7; ++c) tmem_ld16_async(t_row + (uint32_t)(COL0 + 16 * c), acc[c]);
+#pragma unroll
+  for (int c = 0; c < 7; ++c) tmem_ld_wait16(acc[c]);
+  tc_fence_before_sync();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(tempty_bar);
+  if (ti >= p.Wp) return;
+  float* o = p.out + ((size_t)b * kSpecNodes) * p.Wp + ti;
+#pragma unroll
+  for (int f = 0; f < NFI; ++f) {
+    float m = 0.f;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+      const int col = 9 * (FI0 + f) + q - COL0;      // compile-time after unrolling
+      m = fmaxf(m, fabsf(__uint_as_float(acc[col >> 4][col & 15])));
+    }
+    m *= 1.f / (kFtScale * kFtScale);                // undo the 2^10 operand scales (exact)
+    o[(size_t)(FI0 + f) * p.Wp] = ft_selu(fmaf(m, p.bn_scale, p.bn_shift));
+  }
+}
+
+__global__ void __launch_bounds__(kFtThreads, 1)
+sinc_frontend_tc_kernel(const FrontTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* s_b = smem;                                         // [2][9][kFtBChunk]
+  uint8_t* s_a = s_b + 2 * kFtKC * kFtBChunk;                  // [9][2][kFtAChunk]  (kc, hi|lo)
+  __half* s_x = reinterpret_cast<__half*>(s_a + 2 * kFtKC * kFtAChunk);   // 4 staged copies of the segment
+  constexpr int XLEN = kFtSeg + 16;
+  __half* xh0 = s_x;                 // hi, xh0[i] = hi(x[g0+i])
+  __half* xh1 = s_x + XLEN;          // hi shifted by one sample: xh1[i] = xh0[i+1]
+  __half* xl0 = s_x + 2 * XLEN;
+  __half* xl1 = s_x + 3 * XLEN;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_x + 4 * XLEN);
+  uint64_t* afull = bars;            // [9]
+  uint64_t* aempty = bars + kFtKC;   // [9]
+  uint64_t* tfull = bars + 2 * kFtKC;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = p.B * p.n_tiles_per_utt;
+
+  for (int i = threadIdx.x; i < 2 * kFtKC * kFtBChunk / 16; i += kFtThreads)
+    reinterpret_cast<uint4*>(s_b)[i] = __ldg(reinterpret_cast<const uint4*>(p.bimg) + i);
+  fence_proxy_async_smem();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kFtKC; ++i) {
+      mbar_init(&afull[i], kFtProdWarps);
+      mbar_init(&aempty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_ptr);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 1) {
+    // =============================== MMA issuer ==================================
+    const bool leader = elect_one();
+    const uint32_t a_base = smem_u32(s_a), b_base = smem_u32(s_b);
+    constexpr uint32_t IDESC = umma_idesc_f16(128, kFtN);
+    int tcount = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
+      const int buf = tcount & 1;
+      mbar_wait(&tempty[buf], ((tcount >> 1) & 1) ^ 1);
+      tc_fence_after_sync();
+      const uint32_t d = tmem_base + (uint32_t)(buf * kFtBufCols);
+      for (int kc = 0; kc < kFtKC; ++kc) {
+        mbar_wait(&afull[kc], tcount & 1);
+        tc_fence_after_sync();
+        if (leader) {
+          const uint64_t a_hi = umma_desc_noswz(a_base + (uint32_t)((2 * kc) * kFtAChunk));
+          const uint64_t a_lo = umma_desc_noswz(a_base + (uint32_t)((2 * kc + 1) * kFtAChunk));
+          const uint64_t b_hi = umma_desc_noswz(b_base + (uint32_t)(kc * kFtBChunk));
+          const uint64_t b_lo = umma_desc_noswz(b_base + (uint32_t)((kFtKC + kc) * kFtBChunk));
+          umma_f16(d, a_hi, b_hi, IDESC, kc > 0 ? 1u : 0u);
+          umma_f16(d, a_lo, b_hi, IDESC, 1);
+          umma_f16(d, a_hi, b_lo, IDESC, 1);
+          umma_commit(&aempty[kc]);
+        }
+        __syncwarp();
+      }
+      if (leader) umma_commit(&tfull[buf]);
+      __syncwarp();
+    }
+  } else if (warp >= 2 && warp < 10) {
+    // =============================== epilogue ====================================
+    const int quad = warp & 3, half = (warp - 2) >> 2;
+    int tcount = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
+      const int b = t / p.n_tiles_per_utt, tile = t % p.n_tiles_per_utt;
+      const int buf = tcount & 1;
+      const int ti = tile * kFtTile + quad * 32 + lane;
+      mbar_wait(&tfull[buf], (tcount >> 1) & 1);
+      tc_fence_after_sync();
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kFtBufCols);
+      if (half == 0) front_epilogue<0>(t_row, p, b, ti, &tempty[buf], lane);
+      else front_epilogue<1>(t_row, p, b, ti, &tempty[buf], lane);
+    }
+  } else if (warp >= 10) {
+    // ============ A-operand producers: stage the waveform segment, build the Hankel-like tile ============
+    const int ptid = threadIdx.x - 320;          // 0..127 == tile row
+    int tcount = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
+      const int b = t / p.n_tiles_per_utt, tile = t % p.n_tiles_per_utt;
+      const size_t g0 = (size_t)3 * tile * kFtTile;     // first sample of the segment
+      const float* xb = p.x + (size_t)b * p.L;
+      asm volatile("bar.sync 2, %0;" ::"n"(32 * kFtProdWarps) : "memory");   // previous tile fully built
+      for (int i = ptid; i < kFtSeg + 1; i += 32 * kFtProdWarps) {
+        const size_t g = g0 + i;
+        const float v = g < (size_t)p.L ? __ldg(xb + g) * kFtScale : 0.f;
+        const float vc = fminf(fmaxf(v, -65504.f), 65504.f);
+        const __half h = __float2half_rn(vc);
+        const __half l = __float2half_rn(vc - __half2float(h));
+        xh0[i] = h;
+        xl0[i] = l;
+        if (i > 0) { xh1[i - 1] = h; xl1[i - 1] = l; }
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(32 * kFtProdWarps) : "memory");
+      // row ptid, K halves [8q, 8q+8) = samples 3*ptid + 8q ...; pick the copy that makes the start even
+      const int start0 = 3 * ptid;
+      const bool odd = start0 & 1;
+      const uint32_t* srch = reinterpret_cast<const uint32_t*>(odd ? xh1 : xh0) + ((start0 - (odd ? 1 : 0)) >> 1);
+      const uint32_t* srcl = reinterpret_cast<const uint32_t*>(odd ? xl1 : xl0) + ((start0 - (odd ? 1 : 0)) >> 1);
+      const uint32_t row_off = (uint32_t)((ptid >> 3) * 256 + (ptid & 7) * 16);
+      for (int kc = 0; kc < kFtKC; ++kc) {
+        mbar_wait(&aempty[kc], (tcount & 1) ^ 1);
+        uint8_t* ah = s_a + (size_t)(2 * kc) * kFtAChunk + row_off;
+        uint8_t* al = ah + kFtAChunk;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {                 // the two 16-byte K halves of the chunk
+          const int w = (16 * kc + 8 * hf) >> 1;         // word offset of these 8 halves
+          *reinterpret_cast<uint4*>(ah + hf * 128) = make_uint4(srch[w], srch[w + 1], srch[w + 2], srch[w + 3]);
+          *reinterpret_cast<uint4*>(al + hf * 128) = make_uint4(srcl[w], srcl[w + 1], srcl[w + 2], srcl[w + 3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&afull[kc]);
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// filter operand image from the device-built bank (copied back once at finalize)
+int tc_front_finalize(aasist_handle* h, uint8_t** bimg_dev) {
+  const int F = h->cfg.n_filters, K = h->taps;
+  if (K > 16 * kFtKC - 2 || F / 3 != kSpecNodes) {
+    set_error("f16x3 sinc front end supports up to %d taps and 69..71 filters", 16 * kFtKC - 2);
+    return AASIST_E_INVALID;
+  }
+  std::vector<float> bank((size_t)F * K);
+  AASIST_CUDA(cudaMemcpy(bank.data(), h->bank, sizeof(float) * bank.size(), cudaMemcpyDeviceToHost));
+  std::vector<uint8_t> img((size_t)2 * kFtKC * kFtBChunk, 0);
+  for (int n = 0; n < 9 * kSpecNodes; ++n) {
+    const int fi = n / 9, df = (n % 9) / 3, s = n % 3;
+    const int f = 3 * fi + df;
+    for (int k = 0; k < K; ++k) {
+      const int kp = k + s;                                   // H[n][k'] = h[f][k' - s]
+      const float w = bank[(size_t)f * K + k] * kFtScale;
+      const __half hi = __float2half_rn(w);
+      const __half lo = __float2half_rn(w - __half2float(hi));
+      const int kc = kp / 16, kb = (kp % 16) * 2;
+      const size_t off = (size_t)kc * kFtBChunk + (size_t)(n / 8) * 256 + (size_t)(kb / 16) * 128 +
+                         (size_t)(n % 8) * 16 + (size_t)(kb % 16);
+      memcpy(&img[off], &hi, 2);
+      memcpy(&img[(size_t)kFtKC * kFtBChunk + off], &lo, 2);
+    }
+  }
+  if (*bimg_dev) cudaFree(*bimg_dev);
+  *bimg_dev = nullptr;
+  AASIST_CUDA(cudaMalloc(bimg_dev, img.size()));
+  AASIST_CUDA(cudaMemcpy(*bimg_dev, img.data(), img.size(), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int launch_frontend_tc(aasist_handle* h, const uint8_t* bimg, int sm_count, const float* x, int B, int L,
+                       float* out, cudaStream_t st) {
+  const int Wp = (L - h->taps + 1) / 3;
+  if (Wp < 1) {
+    set_error("input length %d too short for a %d-tap filter bank", L, h->taps);
+    return AASIST_E_INVALID;
+  }
+  FrontTcParams p;
+  p.x = x; p.out = out; p.bimg = bimg; p.B = B; p.L = L; p.Wp = Wp;
+  p.n_tiles_per_utt = (Wp + kFtTile - 1) / kFtTile;
+  p.bn_scale = h->bn0_scale; p.bn_shift = h->bn0_shift;
+  const size_t smem = 1024 + 2 * kFtKC * kFtBChunk + 2 * kFtKC * kFtAChunk + 4 * (kFtSeg + 16) * 2 + 256;
+  AASIST_CUDA(cudaFuncSetAttribute(sinc_frontend_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = std::min(B * p.n_tiles_per_utt, sm_count);
+  {
+    LaunchSpan span(h, "sinc_frontend_tc", st);
+    sinc_frontend_tc_kernel<<<grid, kFtThreads, smem, st>>>(p);
+  }
+  AASIST_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace aasist

@@ -12,4 +12,8 @@ int tc_frontend_to_f32(aasist_handle* h, const float* x, int B, int L, float* ou
                        int64_t ws_bytes, cudaStream_t st);
 int tc_block_f32io(aasist_handle* h, int enc, int index, const float* in, int B, int W, float* out,
                    void* ws, int64_t ws_bytes, cudaStream_t st);
+// tensor-core sinc front end (frontend_tc.cu)
+int tc_front_finalize(aasist_handle* h, uint8_t** bimg_dev);
+int launch_frontend_tc(aasist_handle* h, const uint8_t* bimg, int sm_count, const float* x, int B, int L,
+                       float* out, cudaStream_t st);
 }  // namespace aasist

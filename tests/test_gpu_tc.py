@@ -24,6 +24,20 @@ def _g():
 
 
 @pytest.mark.parametrize("name", ["AASIST", "AASIST-L"])
+def test_tc_sinc_frontend_stage(name):
+    g = _g()
+    x = O.speech_like(2, 64600, 3)
+    x[1] *= 8.0                                   # louder utterance: exercises the fp16 operand range
+    taps = g.oracle_taps(name, x)
+    out = g.stage_frontend(g.native_model(name, "f16x3"), x.to(g.DEV))
+    ref = taps["frontend"]
+    err = (out.cpu() - ref).abs().max().item()
+    print(json.dumps({"model": name, "frontend_abs_err": err, "ref_max": ref.abs().max().item()}))
+    # first_bn multiplies the pooled |sinc| output by ~121: 1e-4 here is ~1e-6 on the conv output
+    assert err <= 2e-4 * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.parametrize("name", ["AASIST", "AASIST-L"])
 def test_tc_encoder_blocks_stagewise(name):
     g = _g()
     x = O.speech_like(2, 64600, 4)
