@@ -162,6 +162,7 @@ def run_native(args):
     if args.gpus > 1 and world == 1:
         raise SystemExit("for --gpus N>1 launch with: python -m torch.distributed.run --nnodes=1 "
                          "--nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...")
+    os.environ["NCCL_DEBUG"] = os.environ.get("AASIST_NCCL_DEBUG", "WARN")   # keep stdout to ONE json line
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
