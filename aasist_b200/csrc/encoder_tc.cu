@@ -31,7 +31,11 @@ constexpr int kSlabBytes = 17 * 1024;       // 130 rows x 128 B, rounded up to t
 constexpr int kEpiWarps = 8;                // two warps per TMEM lane quadrant (column halves)
 constexpr int kTcThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxSlots = 8;
-constexpr int kChunkTc = 128;               // utterances per encoder pass (bounds scratch)
+static int tc_chunk() {                     // utterances per encoder pass (bounds scratch: ~95 MB each)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("AASIST_TC_CHUNK"); v = e ? std::max(1, atoi(e)) : 128; }
+  return v;
+}
 
 enum { TC_CONV1 = 0, TC_CONV2_ID = 1, TC_CONV2_DS = 2, TC_CONV2_Z = 3 };
 
@@ -859,7 +863,7 @@ static inline size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 size_t tc_workspace_bytes(const aasist_handle* h, int B, int L) {
   TcPlan pl;
   make_tc_plan(h, L, pl);
-  size_t nb = std::min(B, kChunkTc);
+  size_t nb = std::min(B, tc_chunk());
   return al256(pl.z * nb) + al256(pl.mid * nb) + 2 * al256(pl.act * nb) + 1024;
 }
 
@@ -953,7 +957,7 @@ static int run_block_tc(aasist_handle* h, int enc, int index, const __half* in_p
 int tc_encode(aasist_handle* h, const float* x, int B, int L, float** enc_out, void* ws, cudaStream_t st) {
   TcPlan pl;
   make_tc_plan(h, L, pl);
-  const int nbmax = std::min(B, kChunkTc);
+  const int nbmax = std::min(B, tc_chunk());
   char* w = (char*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
   float* z = (float*)w;
   w += al256(pl.z * nbmax);

@@ -44,6 +44,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// wait with sleep back-off: for warps that have slack (epilogue, operand producers) and share
+// an SMSP with math warps -- a sleeping warp issues nothing, a polling one steals issue slots
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t ns = 64;
+  while (true) {
+    __nanosleep(ns);
+    if (mbar_try_wait(bar, parity)) return;
+    if (ns < 512) ns *= 2;
+  }
+}
+
 // generic-proxy writes to smem -> visible to the async proxy (TMA / tcgen05 operand fetch)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
