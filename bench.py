@@ -263,16 +263,29 @@ def run_native(args):
     roofline = None
     if top is not None:
         from aasist_b200 import workmodel
-        flops = workmodel.kernel_flops(name, top["kernel"], B, L_SAMPLES)      # algorithmic FLOPs / step
+        flops_step = workmodel.kernel_flops(name, top["kernel"], B, L_SAMPLES)   # algorithmic FLOPs / step
+        n_launch = max(1, top["launches"] // args.steps)                          # launches of it per step
+        avg_launch_ms = top["ms"] / max(1, top["launches"])
         peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
-        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PF sustained (B200_PROFILING.md)"
-        ach = flops * args.steps / (top["ms"] * 1e-3) / 1e12
+        peak_src = ("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks
+                    else "fallback 1.4 PF sustained (B200_PROFILING.md)")
+        ach = (flops_step / n_launch) / (avg_launch_ms * 1e-3) / 1e12
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            if name == "AASIST" and B // n_launch == tr.get("utterances_per_launch"):
+                traffic = tr.get(top["kernel"])
+        except Exception:
+            pass
         roofline = {"bound": "tensor", "kernel": top["kernel"], "achieved": ach, "peak": peak_tf,
-                    "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                    "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
                     "peak_source": peak_src, "share_of_step": top["ms"] / total_kernel_ms,
-                    "flops_per_launch_group": flops,
-                    "note": "achieved = algorithmic (2xMAC, fp32-reference) FLOPs of this kernel's launches "
-                            "per step / their CUDA-event time; fp32 path runs on CUDA cores, f16x3 executes 3 MMAs per MAC"}
+                    "flops_per_launch": flops_step / n_launch, "launches_per_step": n_launch,
+                    "avg_launch_ms": avg_launch_ms,
+                    "note": "achieved = ALGORITHMIC FLOPs per launch (2xMAC of the reference fp32 ops, "
+                            "aasist_b200/workmodel.py) / mean CUDA-event launch time; the f16x3 path executes 3 "
+                            "tcgen05 MMAs per reference MAC, so tensor-pipe work is 3x this figure; traffic = ncu "
+                            "dram bytes per launch (profiles/ncu_traffic.json)"}
     line = {
         "metric": "AASIST utterances/sec (4 s, 64600 samples)", "value": value, "unit": "utt/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
