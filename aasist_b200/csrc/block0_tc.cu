@@ -1,0 +1,501 @@
+// Encoder block 0 (reference models/RawNetGatSpoofST.py:258-278 with nb_filts=[1,32], first=True),
+// fully on the tensor cores, one kernel:
+//
+//   z (B,23,W) fp32  --conv1 k(2,3) pad(1,1) + bn2 + SELU-->  v (32 ch, 24 rows)   [never leaves the SM]
+//                    --conv2 k(2,3) pad(0,1) + conv_downsample(z) k(1,3) + max-pool 3-->  pairs [B][23][3][Jn][64]
+//
+// conv1 has ONE input channel (K = 6 taps): as an MMA it is a single K=16 chunk whose A operand is an
+// im2col tile of z in fp16 pairs, [z_hi taps(6) | z_lo taps(6) | 0(4)], built by two producer warps;
+// B1 = [w_hi(6) | w_hi(6) | 0], B1' = [w_lo(6) | 0] give the three split products in two MMAs.
+// Its accumulator D1 (128 x 32, TMEM) is turned into conv2's A operand by 8 "transformer" warps:
+// tcgen05.ld -> +bias -> SELU -> zero outside [0,W) -> fp16 hi/lo -> 128B-swizzled rows of the same
+// shared-memory ring the TMA would fill for the later blocks.  conv2 then runs exactly like
+// conv_tc_kernel (strip-mined, two passes per input row, phase-split pooling), and conv_downsample
+// (1 -> 32 channels, 3 taps) is six more K=16 MMAs per output row on a second im2col tile.
+// Work item: (utterance, strip of 126 pooled columns): conv2 needs v rows j0-1 .. j0+126 = one M=128 tile.
+//
+// warps: 0 idle | 1 MMA issuer + TMEM owner | 2-9 epilogue | 10-17 transformers | 18-19 im2col producers
+#include <algorithm>
+
+#include "ptx.cuh"
+#include "tc.cuh"
+
+namespace aasist {
+
+using namespace ptx;
+
+constexpr int kB0Strip = 126;               // valid pooled columns per strip
+constexpr int kB0Slab = 17 * 1024;          // one v tile (136 rows x 128 B, SWIZZLE_128B)
+constexpr int kB0A1Bytes = 17 * 256;        // im2col tile: 136 rows x 32 B, no-swizzle canonical
+constexpr int kB0A1Stride = 4608;
+constexpr int kB0DsBytes = 16 * 256;        // downsample im2col tile: 128 rows x 32 B
+constexpr int kB0NA1 = 4, kB0ND1 = 6, kB0NDS = 2;
+constexpr int kB0Threads = 640;
+constexpr int kB0ZW = 392;                  // z columns staged per strip: 3*j0-4 .. 3*j0+387
+constexpr int kB0W2Bytes = 6 * 32 * 128;    // conv2 weight image (6 taps x [32 rows x 128 B])
+constexpr int kB0ImgBytes = kB0W2Bytes + 2 * 1024 + 6 * 1024;   // + B1, B1' + 3 x (Bds, Bds')
+
+struct Block0Params {
+  const float* z;          // (B,23,W)
+  __half* out;             // [B][23][3][Jn][64]
+  const uint8_t* wimg;     // kB0ImgBytes
+  const float* b1;         // [32] conv1 bias (bn2 folded)
+  const float* b2;         // [32] conv2 bias + downsample bias
+  int B, W, J, Wo, Jn, n_jt, n_slots;
+};
+
+__device__ __forceinline__ uint64_t b0_desc_noswz(uint32_t smem_addr) {   // LBO 128 B, SBO 256 B
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) |
+         ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ float b0_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float b0_selu(float v) {
+  const float e = b0_ex2(v * 1.4426950408889634f);
+  const float n = fminf(fmaf(e, kSeluScale * kSeluAlpha, -(kSeluScale * kSeluAlpha)), 0.f);
+  return fmaf(fmaxf(v, 0.f), kSeluScale, n);
+}
+template <bool LOWER_BOUNDED>
+__device__ __forceinline__ void b0_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  a = fminf(a, 65504.f);
+  b = fminf(b, 65504.f);
+  if (!LOWER_BOUNDED) {
+    a = fmaxf(a, -65504.f);
+    b = fmaxf(b, -65504.f);
+  }
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 f = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+__global__ void __launch_bounds__(kB0Threads, 1)
+block0_tc_kernel(const Block0Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* s_w = smem;                                         // weight images
+  uint8_t* s_ring = smem + kB0ImgBytes;                        // v tiles
+  uint8_t* s_a1 = s_ring + (size_t)p.n_slots * kB0Slab;        // conv1 im2col ring
+  uint8_t* s_ds = s_a1 + kB0NA1 * kB0A1Stride;                 // downsample im2col ring
+  float* s_z = reinterpret_cast<float*>(s_ds + kB0NDS * kB0DsBytes);   // [23][kB0ZW] fp32 window of z
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_z + 23 * kB0ZW);
+  uint64_t* full = bars;                   // [8]  v tile written (8 transformer warps)
+  uint64_t* empty = bars + 8;              // [8]  v tile consumed (tcgen05.commit)
+  uint64_t* tfull = bars + 16;             // [2]  conv2 accumulators complete
+  uint64_t* tempty = bars + 18;            // [2]  ... drained (8 epilogue warps)
+  uint64_t* a1full = bars + 20;            // [4]  (2 producer warps)
+  uint64_t* a1empty = bars + 24;           // [4]
+  uint64_t* d1full = bars + 28;            // [6]  conv1 accumulator complete
+  uint64_t* d1empty = bars + 34;           // [6]  ... drained (8 transformer warps)
+  uint64_t* dsfull = bars + 40;            // [2]
+  uint64_t* dsempty = bars + 42;           // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 44);
+  float* s_b1 = reinterpret_cast<float*>(bars + 46);     // [32] conv1 bias, broadcast reads by the transformers
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_strips = p.B * p.n_jt;
+
+  for (int i = threadIdx.x; i < kB0ImgBytes / 16; i += kB0Threads)
+    reinterpret_cast<uint4*>(s_w)[i] = __ldg(reinterpret_cast<const uint4*>(p.wimg) + i);
+  // rows 128..135 of a v tile are read (by discarded accumulator rows) but never written: keep them finite
+  for (int i = threadIdx.x; i < p.n_slots * kB0Slab / 16; i += kB0Threads)
+    reinterpret_cast<uint4*>(s_ring)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x < 32) s_b1[threadIdx.x] = __ldg(p.b1 + threadIdx.x);
+  fence_proxy_async_smem();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 8; ++i) { mbar_init(&full[i], 4); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    for (int i = 0; i < kB0NA1; ++i) { mbar_init(&a1full[i], 3); mbar_init(&a1empty[i], 1); }
+    for (int i = 0; i < kB0ND1; ++i) { mbar_init(&d1full[i], 1); mbar_init(&d1empty[i], 4); }
+    for (int i = 0; i < kB0NDS; ++i) { mbar_init(&dsfull[i], 3); mbar_init(&dsempty[i], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_ptr);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+  constexpr int D1_COL0 = 192;             // TMEM: [0,192) conv2 accumulators (2 x 3 x 32), [192,384) D1 ring
+
+  if (warp == 1) {
+    // ======================================= MMA issuer =======================================
+    const bool leader = elect_one();
+    const uint32_t w_base = smem_u32(s_w), ring_base = smem_u32(s_ring);
+    const uint32_t a1_base = smem_u32(s_a1), ds_base = smem_u32(s_ds);
+    const uint32_t b1_addr = w_base + kB0W2Bytes, b1p_addr = b1_addr + 1024, bds_addr = b1_addr + 2048;
+    constexpr uint32_t IDESC = umma_idesc_f16(128, 32);
+    int n1 = 0;                            // conv1 tiles issued
+    int slot = 0;
+    uint32_t phase = 0;
+    int nstart = 0, nds = 0;
+
+    auto issue_conv1_row = [&]() {         // the three phase tiles of one v row
+      for (int phi = 0; phi < 3; ++phi, ++n1) {
+        const int ka = n1 % kB0NA1, kd = n1 % kB0ND1;
+        mbar_wait(&a1full[ka], (n1 / kB0NA1) & 1);
+        mbar_wait(&d1empty[kd], ((n1 / kB0ND1) & 1) ^ 1);
+        tc_fence_after_sync();
+        if (leader) {
+          const uint64_t a = b0_desc_noswz(a1_base + (uint32_t)(ka * kB0A1Stride));
+          const uint32_t d = tmem_base + (uint32_t)(D1_COL0 + 32 * kd);
+          umma_f16(d, a, b0_desc_noswz(b1_addr), IDESC, 0);
+          umma_f16(d, a, b0_desc_noswz(b1p_addr), IDESC, 1);
+          umma_commit(&a1empty[ka]);
+          umma_commit(&d1full[kd]);
+        }
+        __syncwarp();
+      }
+    };
+    // conv2 MMAs of one v tile: pool phases that read the same A rows share one wider-N MMA
+    // (weights stored with taps dw = 2,1,0 contiguous; see conv_tc_kernel::issue_group)
+    auto mma3 = [&](uint32_t d_tmem, uint32_t a_row, uint32_t w_row, int ntaps, bool fresh) {
+      const uint32_t idesc = ntaps == 3 ? umma_idesc_f16(128, 96) : (ntaps == 2 ? umma_idesc_f16(128, 64) : IDESC);
+      const uint64_t a_hi = umma_desc_sw128(a_row), a_lo = umma_desc_sw128(a_row + 64);
+      const uint64_t w_hi = umma_desc_sw128(w_row), w_lo = umma_desc_sw128(w_row + 64);
+#pragma unroll
+      for (int kc = 0; kc < 2; ++kc) {
+        umma_f16(d_tmem, a_hi + 2 * kc, w_hi + 2 * kc, idesc, (kc > 0 || !fresh) ? 1u : 0u);
+        umma_f16(d_tmem, a_lo + 2 * kc, w_hi + 2 * kc, idesc, 1);
+        umma_f16(d_tmem, a_hi + 2 * kc, w_lo + 2 * kc, idesc, 1);
+      }
+    };
+    auto issue_group = [&](int slot_i, int dh, int phi, int buf, bool fresh) {
+      const uint32_t a_slot = ring_base + (uint32_t)slot_i * kB0Slab;
+      const uint32_t wb = w_base + (uint32_t)(dh * 3 * 4096);
+      const uint32_t d0 = tmem_base + (uint32_t)(buf * 96);
+      if (phi == 1) {
+        mma3(d0, a_slot + 128, wb, 3, fresh);
+      } else if (phi == 0) {
+        mma3(d0, a_slot + 128, wb + 4096, 2, fresh);
+        mma3(d0 + 64, a_slot + 256, wb, 1, fresh);
+      } else {
+        mma3(d0 + 32, a_slot + 128, wb, 2, fresh);
+        mma3(d0, a_slot, wb + 8192, 1, fresh);
+      }
+    };
+    auto advance = [&](int& sl, uint32_t& ph) {
+      if (++sl == p.n_slots) { sl = 0; ph ^= 1; }
+    };
+
+    for (int t = blockIdx.x; t < n_strips; t += gridDim.x) {
+      int buf_open = 0;
+      issue_conv1_row();                                         // v row 0
+      for (int r = 0; r < 24; ++r) {
+        if (r < 23) issue_conv1_row();                           // v row r+1 (one row ahead of conv2)
+        const bool has_o1 = r >= 1, has_o0 = r <= 22;
+        int sl[3];
+        uint32_t ph[3];
+        {
+          int s2 = slot;
+          uint32_t p2 = phase;
+          for (int i = 0; i < 3; ++i) { sl[i] = s2; ph[i] = p2; advance(s2, p2); }
+        }
+        for (int phi = 0; phi < 3; ++phi) {                      // pass 1: dh=1 completes output row r-1
+          mbar_wait(&full[sl[phi]], ph[phi]);
+          tc_fence_after_sync();
+          if (has_o1 && leader) issue_group(sl[phi], 1, phi, buf_open, false);
+          __syncwarp();
+        }
+        if (has_o1) {
+          if (leader) umma_commit(&tfull[buf_open]);
+          __syncwarp();
+        }
+        if (has_o0) {                                            // pass 2: dh=0 starts output row r
+          buf_open = nstart & 1;
+          mbar_wait(&tempty[buf_open], ((nstart >> 1) & 1) ^ 1);
+          tc_fence_after_sync();
+          ++nstart;
+          for (int phi = 0; phi < 3; ++phi) {
+            if (leader) {
+              issue_group(sl[phi], 0, phi, buf_open, phi == 0);
+              umma_commit(&empty[sl[phi]]);
+            }
+            __syncwarp();
+          }
+          // conv_downsample of z row r into the same accumulators (K = 16 im2col chunk, one B per pool phase)
+          const int kq = nds % kB0NDS;
+          mbar_wait(&dsfull[kq], (nds / kB0NDS) & 1);
+          tc_fence_after_sync();
+          if (leader) {
+            const uint64_t a = b0_desc_noswz(ds_base + (uint32_t)(kq * kB0DsBytes));
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+              const uint32_t d_tmem = tmem_base + (uint32_t)((buf_open * 3 + s) * 32);
+              umma_f16(d_tmem, a, b0_desc_noswz(bds_addr + (uint32_t)(2 * s) * 1024), IDESC, 1);
+              umma_f16(d_tmem, a, b0_desc_noswz(bds_addr + (uint32_t)(2 * s + 1) * 1024), IDESC, 1);
+            }
+            umma_commit(&dsempty[kq]);
+          }
+          __syncwarp();
+          ++nds;
+        } else {
+          for (int phi = 0; phi < 3; ++phi) {
+            if (leader) umma_commit(&empty[sl[phi]]);
+            __syncwarp();
+          }
+        }
+        for (int i = 0; i < 3; ++i) advance(slot, phase);
+      }
+    }
+  } else if (warp >= 2 && warp < 10) {
+    // ======================================= epilogue =========================================
+    const int quad = warp & 3, half = (warp - 2) >> 2;
+    const int m = quad * 32 + lane;                              // accumulator row
+    const int col0 = half * 16;
+    float bias[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) bias[i] = __ldg(p.b2 + col0 + i);
+    int tcount = 0;
+    for (int t = blockIdx.x; t < n_strips; t += gridDim.x) {
+      const int jt = t % p.n_jt, b = t / p.n_jt;
+      const int j = jt * kB0Strip + m;
+      const bool store = m < kB0Strip && j / 3 < p.Jn;
+      const bool valid = j < p.Wo;
+      for (int h = 0; h < 23; ++h, ++tcount) {
+        const int buf = tcount & 1;
+        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 96 + col0);
+        mbar_wait(&tfull[buf], (tcount >> 1) & 1);
+        tc_fence_after_sync();
+        uint32_t acc[3][16];
+#pragma unroll
+        for (int s = 0; s < 3; ++s) tmem_ld16_async(t_row + (uint32_t)(s * 32), acc[s]);
+#pragma unroll
+        for (int s = 0; s < 3; ++s) tmem_ld_wait16(acc[s]);
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[buf]);
+        if (!store) continue;
+        uint32_t hw[8], lw[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float x0 = fmaxf(fmaxf(__uint_as_float(acc[0][2 * i]), __uint_as_float(acc[1][2 * i])),
+                           __uint_as_float(acc[2][2 * i])) + bias[2 * i];
+          float x1 = fmaxf(fmaxf(__uint_as_float(acc[0][2 * i + 1]), __uint_as_float(acc[1][2 * i + 1])),
+                           __uint_as_float(acc[2][2 * i + 1])) + bias[2 * i + 1];
+          if (!valid) { x0 = 0.f; x1 = 0.f; }
+          b0_split2<false>(x0, x1, hw[i], lw[i]);
+        }
+        __half* o = p.out + ((((size_t)b * 23 + h) * 3 + (j % 3)) * p.Jn + j / 3) * 64 + col0;
+        uint4* oh = reinterpret_cast<uint4*>(o);
+        uint4* ol = reinterpret_cast<uint4*>(o + 32);
+        oh[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        oh[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+        ol[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        ol[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+      }
+    }
+  } else if (warp >= 10 && warp < 18) {
+    // ============ transformers: D1 (TMEM) -> bias, SELU, zero-pad mask, fp16 pairs -> swizzled v tile ============
+    // two groups of four warps (one warp per TMEM lane quadrant) take alternate tiles, so two tiles
+    // are in flight; a thread owns one tile row and all 32 channels.
+    const int quad = warp & 3, grp = (warp - 10) >> 2;
+    const int jj = quad * 32 + lane;                             // tile row
+    const uint32_t row_off = (uint32_t)jj * 128;
+    const uint32_t sw = (uint32_t)(jj & 7);
+    const float* b1s = s_b1;
+    int n = 0, slot = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < n_strips; t += gridDim.x) {
+      const int jt = t % p.n_jt;
+      const int j = jt * kB0Strip - 1 + jj;
+      for (int r = 0; r < 24; ++r) {
+        for (int phi = 0; phi < 3; ++phi, ++n) {
+          if ((n & 1) == grp) {
+            const int kd = n % kB0ND1;
+            const int pos = 3 * j + phi;
+            const bool valid = j >= 0 && pos < p.W;              // conv2 zero-pads v itself
+            mbar_wait(&d1full[kd], (n / kB0ND1) & 1);
+            tc_fence_after_sync();
+            uint32_t acc[2][16];
+            const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(D1_COL0 + 32 * kd);
+            tmem_ld16_async(ta, acc[0]);
+            tmem_ld16_async(ta + 16, acc[1]);
+            tmem_ld_wait16(acc[0]);
+            tmem_ld_wait16(acc[1]);
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&d1empty[kd]);
+            uint32_t hw[16], lw[16];
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float2 bb = *reinterpret_cast<const float2*>(b1s + c * 16 + 2 * i);
+                float x0 = b0_selu(__uint_as_float(acc[c][2 * i]) + bb.x);
+                float x1 = b0_selu(__uint_as_float(acc[c][2 * i + 1]) + bb.y);
+                if (!valid) { x0 = 0.f; x1 = 0.f; }
+                b0_split2<true>(x0, x1, hw[c * 8 + i], lw[c * 8 + i]);
+              }
+            mbar_wait(&empty[slot], phase ^ 1);
+            uint8_t* row = s_ring + (size_t)slot * kB0Slab + row_off;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {                        // chunks 0..3 = hi channels, 4..7 = lo channels
+              *reinterpret_cast<uint4*>(row + (((uint32_t)q ^ sw) << 4)) =
+                  make_uint4(hw[4 * q], hw[4 * q + 1], hw[4 * q + 2], hw[4 * q + 3]);
+              *reinterpret_cast<uint4*>(row + (((uint32_t)(4 + q) ^ sw) << 4)) =
+                  make_uint4(lw[4 * q], lw[4 * q + 1], lw[4 * q + 2], lw[4 * q + 3]);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[slot]);
+          }
+          if (++slot == p.n_slots) { slot = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 18 || warp == 0) {
+    // ============ im2col producers (warps 0, 18, 19): z taps as fp16 pairs, one 32-byte row per tile row ============
+    const int ptid = warp == 0 ? lane : threadIdx.x - 17 * 32;   // 0..95
+    int n = 0, nds = 0;
+    auto split1 = [](float v, __half& h, __half& l) {
+      v = fminf(fmaxf(v, -65504.f), 65504.f);
+      h = __float2half_rn(v);
+      l = __float2half_rn(v - __half2float(h));
+    };
+    for (int t = blockIdx.x; t < n_strips; t += gridDim.x) {
+      const int jt = t % p.n_jt, b = t / p.n_jt;
+      const int j0 = jt * kB0Strip;
+      const float* zb = p.z + (size_t)b * 23 * p.W;
+      // stage the strip's window of z (columns wz0 .. wz0+kB0ZW) once, asynchronously (4-byte cp.async:
+      // rows of z are not 16-byte aligned), zero outside [0,W)
+      const int wz0 = 3 * j0 - 4;
+      asm volatile("bar.sync 3, 96;" ::: "memory");            // all producer warps are done with the old window
+      for (int i = ptid; i < 23 * kB0ZW; i += 96) {
+        const int row = i / kB0ZW, w = wz0 + i % kB0ZW;
+        if (w >= 0 && w < p.W) {
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(s_z + i)),
+                       "l"(zb + (size_t)row * p.W + w)
+                       : "memory");
+        } else {
+          s_z[i] = 0.f;
+        }
+      }
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      asm volatile("bar.sync 3, 96;" ::: "memory");
+      auto zat = [&](int row, int w) -> float {                  // z[row][w] with conv zero padding
+        if (row < 0 || row > 22) return 0.f;
+        const int c = min(max(w - wz0, 0), kB0ZW - 1);           // clamp only matters for discarded tile rows
+        return s_z[row * kB0ZW + c];
+      };
+      auto conv1_tile = [&](int r, int phi) {
+        const int ka = n % kB0NA1;
+        mbar_wait(&a1empty[ka], ((n / kB0NA1) & 1) ^ 1);
+        uint8_t* dst = s_a1 + ka * kB0A1Stride;
+        for (int jj = ptid; jj < 136; jj += 96) {
+          const int pos = 3 * (j0 - 1 + jj) + phi;
+          __half h[6], l[6];
+#pragma unroll
+          for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+            for (int dw = 0; dw < 3; ++dw) split1(zat(r + dh - 1, pos + dw - 1), h[dh * 3 + dw], l[dh * 3 + dw]);
+          uint8_t* row = dst + (jj >> 3) * 256 + (jj & 7) * 16;
+          *reinterpret_cast<uint4*>(row) =
+              make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(l[0], l[1]));
+          *reinterpret_cast<uint4*>(row + 128) = make_uint4(pack_h2(l[2], l[3]), pack_h2(l[4], l[5]), 0u, 0u);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a1full[ka]);
+        ++n;
+      };
+      auto ds_tile = [&](int h) {
+        const int kq = nds % kB0NDS;
+        mbar_wait(&dsempty[kq], ((nds / kB0NDS) & 1) ^ 1);
+        uint8_t* dst = s_ds + kq * kB0DsBytes;
+        for (int m = ptid; m < 128; m += 96) {
+          const int w0 = 3 * (j0 + m) - 1;                         // taps 3j-1 .. 3j+3
+          __half hh[5], ll[5];
+#pragma unroll
+          for (int i = 0; i < 5; ++i) split1(zat(h, w0 + i), hh[i], ll[i]);
+          uint8_t* row = dst + (m >> 3) * 256 + (m & 7) * 16;
+          *reinterpret_cast<uint4*>(row) = make_uint4(pack_h2(hh[0], hh[1]), pack_h2(hh[2], hh[3]),
+                                                      pack_h2(hh[4], ll[0]), pack_h2(ll[1], ll[2]));
+          *reinterpret_cast<uint4*>(row + 128) = make_uint4(pack_h2(ll[3], ll[4]), 0u, 0u, 0u);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&dsfull[kq]);
+        ++nds;
+      };
+      for (int phi = 0; phi < 3; ++phi) conv1_tile(0, phi);
+      for (int r = 0; r < 24; ++r) {                             // same order as the MMA warp consumes
+        if (r < 23)
+          for (int phi = 0; phi < 3; ++phi) conv1_tile(r + 1, phi);
+        if (r <= 22) ds_tile(r);
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------------
+// no-swizzle canonical K=16 operand row: addr = (n/8)*256 + (k/8)*128 + (n%8)*16 + (k%8)*2
+static void put_k16(std::vector<uint8_t>& img, size_t base, int n, int k, float w, bool lo_part) {
+  const __half hi = __float2half_rn(w);
+  const __half lo = __float2half_rn(w - __half2float(hi));
+  const __half v = lo_part ? lo : hi;
+  const size_t off = base + (size_t)(n / 8) * 256 + (size_t)(k / 8) * 128 + (size_t)(n % 8) * 16 + (size_t)(k % 8) * 2;
+  memcpy(&img[off], &v, 2);
+}
+
+// image = [conv2 weights (built by the caller, kB0W2Bytes)] [B1] [B1'] [Bds(s), Bds'(s)] x 3
+void block0_pack_small(std::vector<uint8_t>& img, const std::vector<float>& w1 /*[6][32] bn folded*/,
+                       const std::vector<float>& wd /*[3][32]*/, int co) {
+  img.resize(kB0ImgBytes, 0);
+  const size_t b1 = kB0W2Bytes, b1p = b1 + 1024, bds = b1 + 2048;
+  for (int o = 0; o < co; ++o) {
+    for (int tp = 0; tp < 6; ++tp) {
+      const float w = w1[tp * 32 + o];
+      put_k16(img, b1, o, tp, w, false);        // z_hi taps  x w_hi
+      put_k16(img, b1, o, 6 + tp, w, false);    // z_lo taps  x w_hi
+      put_k16(img, b1p, o, tp, w, true);        // z_hi taps  x w_lo
+    }
+    // downsample tile columns: [z_hi(3j-1..3j+3) (5) | z_lo (5)]; pool phase s uses taps k = s .. s+2
+    for (int s = 0; s < 3; ++s)
+      for (int dw = 0; dw < 3; ++dw) {
+        const float w = wd[dw * 32 + o];
+        put_k16(img, bds + (size_t)(2 * s) * 1024, o, s + dw, w, false);
+        put_k16(img, bds + (size_t)(2 * s) * 1024, o, 5 + s + dw, w, false);
+        put_k16(img, bds + (size_t)(2 * s + 1) * 1024, o, s + dw, w, true);
+      }
+  }
+}
+
+int block0_image_bytes() { return kB0ImgBytes; }
+int block0_w2_bytes() { return kB0W2Bytes; }
+
+int launch_block0_tc(aasist_handle* h, int sm_count, const uint8_t* wimg, const float* b1, const float* b2,
+                     const float* z, int nb, int W, __half* out, cudaStream_t st) {
+  Block0Params p;
+  p.z = z; p.out = out; p.wimg = wimg; p.b1 = b1; p.b2 = b2;
+  p.B = nb; p.W = W; p.J = (W + 2) / 3; p.Wo = W / 3; p.Jn = (p.Wo + 2) / 3;
+  p.n_jt = (std::max(p.J, 3 * p.Jn) + kB0Strip - 1) / kB0Strip;
+  const int fixed = 1024 + kB0ImgBytes + kB0NA1 * kB0A1Stride + kB0NDS * kB0DsBytes + 23 * kB0ZW * 4 + 512;
+  p.n_slots = std::min(8, (227 * 1024 - fixed) / kB0Slab);
+  if (p.n_slots < 6) {
+    set_error("block0_tc: shared memory budget allows only %d ring slots", p.n_slots);
+    return AASIST_E_INVALID;
+  }
+  const size_t smem = (size_t)fixed + (size_t)p.n_slots * kB0Slab;
+  AASIST_CUDA(cudaFuncSetAttribute(block0_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = std::min(nb * p.n_jt, sm_count);
+  {
+    LaunchSpan span(h, "enc0.fused_conv1_conv2_tc", st);
+    block0_tc_kernel<<<grid, kB0Threads, smem, st>>>(p);
+  }
+  AASIST_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace aasist

@@ -66,6 +66,8 @@ struct BlockTc {
   ConvTc c1, c2;
   float* w1_f32 = nullptr;   // block 0 only: conv1 (bn2 folded) [6][32] fp32
   float* wd_f32 = nullptr;   // block 0 only: conv_downsample [3][32] fp32
+  std::vector<float> w1_host, wd_host;
+  uint8_t* b0_img = nullptr; // block 0 only: conv2 + conv1/downsample K=16 operand images (block0_tc.cu)
 };
 struct TcState {
   BlockTc blocks[2][6];
@@ -276,42 +278,46 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t ring_base = smem_u32(s_ring);
     const bool leader = elect_one();
 
-    // all MMAs of one input tile (phase phi) for tap row dh into accumulator buffer `buf`
-    auto issue_group = [&](int slot_i, int dh, int phi, int buf, bool fresh, bool side) {
-      const uint32_t a_slot = ring_base + (uint32_t)slot_i * SLOT_BYTES;
+    // All MMAs of one input tile (phase phi) for tap row dh into accumulator buffer `buf`.
+    // Pool phase s is served by tap dw with (s + dw - 1) == phi (mod 3), from A rows shifted by
+    // floor((s+dw-1)/3).  The MMA is operand-fetch bound (4 KB of A per instruction), so phases that
+    // read the SAME A rows are merged into one wider-N MMA over contiguous B rows (taps stored 2,1,0):
+    //   phi 1: s=0,1,2 <- dw=2,1,0, shift 0             -> one N = 3*COP group
+    //   phi 0: s=0,1   <- dw=1,0,   shift 0 (N = 2*COP);  s=2 <- dw=2, shift +1 (N = COP)
+    //   phi 2: s=1,2   <- dw=2,1,   shift 0 (N = 2*COP);  s=0 <- dw=0, shift -1 (N = COP)
+    auto mma3 = [&](uint32_t d_tmem, uint32_t a_row, uint32_t w_row, int ntaps, bool fresh, bool side) {
+      const uint32_t idesc = ntaps == 3 ? umma_idesc_f16(128, 3 * COP)
+                                        : (ntaps == 2 ? umma_idesc_f16(128, 2 * COP) : umma_idesc_f16(128, COP));
+      const bool one_slab = side || SLABS == 1;
+      const uint64_t a_hi = umma_desc_sw128(a_row);
+      const uint64_t a_lo = umma_desc_sw128(one_slab ? a_row + 64 : a_row + kSlabBytes);
+      const uint64_t w_hi = umma_desc_sw128(w_row);
+      const uint64_t w_lo = umma_desc_sw128(one_slab ? w_row + 64 : w_row + 3 * COP * 128);
+      const int nkc = one_slab ? 2 : KC;
 #pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int d = (phi - s + 3) % 3;              // input phase phi serves pool phase s via tap dw
-        const int dw = d == 0 ? 1 : (d == 1 ? 2 : 0);
-        const int pp = s + dw - 1;                    // offset of the tap in units of phase steps
-        const int shift = pp < 0 ? -1 : (pp > 2 ? 1 : 0);
-        const uint32_t a_row = a_slot + (uint32_t)(1 + shift) * 128;
-        const uint32_t d_tmem = tmem_base + (uint32_t)((buf * 3 + s) * COP);
-        if (!side) {
-          const uint32_t wt = w_base + (uint32_t)((dh * 3 + dw) * TAP_BYTES);
-          const uint64_t a_hi = umma_desc_sw128(a_row);
-          const uint64_t a_lo = umma_desc_sw128((SLABS == 1) ? a_row + 64 : a_row + kSlabBytes);
-          const uint64_t w_hi = umma_desc_sw128(wt);
-          const uint64_t w_lo = umma_desc_sw128((SLABS == 1) ? wt + 64 : wt + COP * 128);
-#pragma unroll
-          for (int kc = 0; kc < KC; ++kc) {           // +32 B per K chunk == +2 in the descriptor
-            umma_f16(d_tmem, a_hi + 2 * kc, w_hi + 2 * kc, IDESC, (kc > 0 || !fresh) ? 1u : 0u);
-            if (!(p.dbg & 1)) {
-              umma_f16(d_tmem, a_lo + 2 * kc, w_hi + 2 * kc, IDESC, 1);
-              umma_f16(d_tmem, a_hi + 2 * kc, w_lo + 2 * kc, IDESC, 1);
-            }
-          }
-        } else {
-          const uint32_t wt = w_base + (uint32_t)(6 * TAP_BYTES + dw * SIDE_TAP_BYTES);
-          const uint64_t a_hi = umma_desc_sw128(a_row), a_lo = umma_desc_sw128(a_row + 64);
-          const uint64_t w_hi = umma_desc_sw128(wt), w_lo = umma_desc_sw128(wt + 64);
-#pragma unroll
-          for (int kc = 0; kc < 2; ++kc) {
-            umma_f16(d_tmem, a_hi + 2 * kc, w_hi + 2 * kc, IDESC, 1);
-            umma_f16(d_tmem, a_lo + 2 * kc, w_hi + 2 * kc, IDESC, 1);
-            umma_f16(d_tmem, a_hi + 2 * kc, w_lo + 2 * kc, IDESC, 1);
+      for (int kc = 0; kc < KC; ++kc) {               // +32 B per K chunk == +2 in the descriptor
+        if (kc < nkc) {
+          umma_f16(d_tmem, a_hi + 2 * kc, w_hi + 2 * kc, idesc, (kc > 0 || !fresh) ? 1u : 0u);
+          if (!(p.dbg & 1)) {
+            umma_f16(d_tmem, a_lo + 2 * kc, w_hi + 2 * kc, idesc, 1);
+            umma_f16(d_tmem, a_hi + 2 * kc, w_lo + 2 * kc, idesc, 1);
           }
         }
+      }
+    };
+    auto issue_group = [&](int slot_i, int dh, int phi, int buf, bool fresh, bool side) {
+      const uint32_t a_slot = ring_base + (uint32_t)slot_i * SLOT_BYTES;
+      const uint32_t wb = side ? w_base + (uint32_t)(6 * TAP_BYTES) : w_base + (uint32_t)(dh * 3 * TAP_BYTES);
+      const uint32_t d0 = tmem_base + (uint32_t)(buf * 3 * COP);
+      constexpr uint32_t ROWS = COP * 128;            // bytes of one tap's rows
+      if (phi == 1) {
+        mma3(d0, a_slot + 128, wb, 3, fresh, side);
+      } else if (phi == 0) {
+        mma3(d0, a_slot + 128, wb + ROWS, 2, fresh, side);
+        mma3(d0 + 2 * COP, a_slot + 256, wb, 1, fresh, side);
+      } else {
+        mma3(d0 + COP, a_slot + 128, wb, 2, fresh, side);
+        mma3(d0, a_slot, wb + 2 * ROWS, 1, fresh, side);
       }
     };
     auto advance = [&](int& sl, uint32_t& ph) {
@@ -690,7 +696,12 @@ static int make_act_tmap(aasist_handle* h, CUtensorMap* m, const void* base, int
 
 // weight image: per tap, SLABS slabs of [cop rows][128 B], rows 128-byte swizzled like a TMA SW128 tile
 //   cpi == 32: one slab, row = [w_hi(32) | w_lo(32)];  cpi == 64: slab 0 = w_hi(64), slab 1 = w_lo(64)
-static void put_tap(std::vector<uint8_t>& img, size_t tap_off, int cpi, int cop, int n, int k, float w) {
+// Weight image.  Rows are 128-byte-swizzled like a TMA SW128 tile.  For each tap row dh the three
+// column taps are stored in the order dw = 2, 1, 0 with `cop` rows each, so that the B rows of pool
+// phases that share an A tile are contiguous and one wider-N tcgen05.mma serves them (see issue_group).
+//   cpi == 32: row = [w_hi(32) | w_lo(32)];  block of dh = 3*cop rows
+//   cpi == 64: block of dh = [hi: 3*cop rows of w_hi(64)] [lo: 3*cop rows of w_lo(64)]
+static void put_tap(std::vector<uint8_t>& img, size_t base, int cpi, int cop, int dh, int dw, int n, int k, float w) {
   __half hi = __float2half_rn(w);
   __half lo = __float2half_rn(w - __half2float(hi));
   auto put = [&](size_t slab_off, int kk, __half v) {
@@ -699,12 +710,15 @@ static void put_tap(std::vector<uint8_t>& img, size_t tap_off, int cpi, int cop,
     size_t off = slab_off + (size_t)n * 128 + (size_t)((chunk ^ (n & 7)) * 16 + within);
     memcpy(&img[off], &v, 2);
   };
+  const size_t tap = (size_t)(2 - dw) * cop * 128;
   if (cpi == 32) {
-    put(tap_off, k, hi);
-    put(tap_off, 32 + k, lo);
+    const size_t b = base + (size_t)dh * 3 * cop * 128 + tap;
+    put(b, k, hi);
+    put(b, 32 + k, lo);
   } else {
-    put(tap_off, k, hi);
-    put(tap_off + (size_t)cop * 128, k, lo);
+    const size_t b = base + (size_t)dh * 6 * cop * 128 + tap;
+    put(b, k, hi);
+    put(b + (size_t)3 * cop * 128, k, lo);
   }
 }
 
@@ -755,19 +769,21 @@ static int pack_block_tc(aasist_handle* h, const std::string& pfx, int index, Bl
     for (int o = 0; o < co; ++o)
       for (int t = 0; t < 6; ++t) w[t * 32 + o] = (float)((double)w1[(size_t)o * 6 + t] * sc[o]);
     if ((rc = upload_f(&blk.w1_f32, w))) return rc;
+    blk.w1_host = w;
     const auto &wdv = P(".conv_downsample.weight"), &bd = P(".conv_downsample.bias");
     for (int o = 0; o < co; ++o) {
       for (int t = 0; t < 3; ++t) wd[t * 32 + o] = wdv[(size_t)o * 3 + t];
       bias2[o] = (float)((double)b2[o] + (double)bd[o]);
     }
     if ((rc = upload_f(&blk.wd_f32, wd))) return rc;
+    blk.wd_host = wd;
   } else {
     const int tap_bytes = (blk.cpi / 32) * blk.cop * 128;
     std::vector<uint8_t> img((size_t)6 * tap_bytes, 0);
     for (int o = 0; o < co; ++o)
       for (int i = 0; i < ci; ++i)
         for (int t = 0; t < 6; ++t)
-          put_tap(img, (size_t)t * tap_bytes, blk.cpi, blk.cop, o, i,
+          put_tap(img, 0, blk.cpi, blk.cop, t / 3, t % 3, o, i,
                   (float)((double)w1[((size_t)o * ci + i) * 6 + t] * sc[o]));
     blk.c1.wimg_bytes = (int)img.size();
     if ((rc = upload_bytes(&blk.c1.wimg, img))) return rc;
@@ -785,19 +801,23 @@ static int pack_block_tc(aasist_handle* h, const std::string& pfx, int index, Bl
     for (int o = 0; o < co; ++o)
       for (int i = 0; i < co; ++i)
         for (int t = 0; t < 6; ++t)
-          put_tap(img, (size_t)t * tap_bytes, blk.cop, blk.cop, o, i, w2[((size_t)o * co + i) * 6 + t]);
+          put_tap(img, 0, blk.cop, blk.cop, t / 3, t % 3, o, i, w2[((size_t)o * co + i) * 6 + t]);
     if (side) {
       const auto &wdv = P(".conv_downsample.weight"), &bd = P(".conv_downsample.bias");
       for (int o = 0; o < co; ++o) {
         for (int i = 0; i < ci; ++i)
           for (int t = 0; t < 3; ++t)
-            put_tap(img, (size_t)6 * tap_bytes + (size_t)t * blk.cop * 128, 32, blk.cop, o, i,
-                    wdv[((size_t)o * ci + i) * 3 + t]);
+            put_tap(img, (size_t)6 * tap_bytes, 32, blk.cop, 0, t, o, i, wdv[((size_t)o * ci + i) * 3 + t]);
         bias2[o] = (float)((double)b2[o] + (double)bd[o]);
       }
     }
     blk.c2.wimg_bytes = (int)img.size();
     if ((rc = upload_bytes(&blk.c2.wimg, img))) return rc;
+    if (index == 0) {
+      std::vector<uint8_t> img0 = img;            // conv2 taps first, then the small K=16 operands
+      block0_pack_small(img0, blk.w1_host, blk.wd_host, co);
+      if ((rc = upload_bytes(&blk.b0_img, img0))) return rc;
+    }
   }
   if ((rc = upload_f(&blk.c2.bias, bias2))) return rc;
   return 0;
@@ -835,7 +855,7 @@ void tc_destroy(aasist_handle* h) {
     for (int i = 0; i < 6; ++i) {
       BlockTc& b = h->tc->blocks[e][i];
       cudaFree(b.c1.wimg); cudaFree(b.c1.bias); cudaFree(b.c2.wimg); cudaFree(b.c2.bias);
-      cudaFree(b.w1_f32); cudaFree(b.wd_f32);
+      cudaFree(b.w1_f32); cudaFree(b.wd_f32); cudaFree(b.b0_img);
     }
   cudaFree(h->tc->front_bimg);
   delete h->tc;
@@ -941,6 +961,10 @@ static int run_block_tc(aasist_handle* h, int enc, int index, const __half* in_p
   p.n_jt = (std::max(J, std::min(3 * Jn, Wo + 2)) + kTileJ - 1) / kTileJ;
   p.bias = blk.c2.bias; p.out = out_pairs; p.out_f32 = out_f32; p.wimg = blk.c2.wimg; p.wimg_bytes = blk.c2.wimg_bytes;
   if (index == 0) {
+    static int old_b0 = -1;   // AASIST_TC_BLOCK0_CUDA=1: previous variant (conv1 + downsample on CUDA cores)
+    if (old_b0 < 0) { const char* e = getenv("AASIST_TC_BLOCK0_CUDA"); old_b0 = e ? atoi(e) : 0; }
+    if (!old_b0 && !out_f32)
+      return launch_block0_tc(h, h->tc->sm_count, blk.b0_img, blk.c1.bias, blk.c2.bias, z, nb, W, out_pairs, st);
     p.z = z; p.wd = blk.wd_f32; p.w1 = blk.w1_f32; p.b1 = blk.c1.bias;
     rc = launch_conv<32, 32, TC_CONV2_Z>(h, "enc0.fused_conv1_conv2_tc", tmIn, tmIn, p, st);
   } else if (!blk.downsample) {

@@ -1,5 +1,7 @@
 // Tensor-core (tcgen05, fp16 hi/lo split x3) path: entry points used by api.cu.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace aasist {
@@ -16,4 +18,10 @@ int tc_block_f32io(aasist_handle* h, int enc, int index, const float* in, int B,
 int tc_front_finalize(aasist_handle* h, uint8_t** bimg_dev);
 int launch_frontend_tc(aasist_handle* h, const uint8_t* bimg, int sm_count, const float* x, int B, int L,
                        float* out, cudaStream_t st);
+// encoder block 0 fully on tensor cores (block0_tc.cu)
+void block0_pack_small(std::vector<uint8_t>& img, const std::vector<float>& w1, const std::vector<float>& wd, int co);
+int block0_image_bytes();
+int block0_w2_bytes();
+int launch_block0_tc(aasist_handle* h, int sm_count, const uint8_t* wimg, const float* b1, const float* b2,
+                     const float* z, int nb, int W, __half* out, cudaStream_t st);
 }  // namespace aasist
