@@ -15,6 +15,8 @@
 // Work item: (utterance, strip of 126 pooled columns): conv2 needs v rows j0-1 .. j0+126 = one M=128 tile.
 //
 // warps: 0 idle | 1 MMA issuer + TMEM owner | 2-9 epilogue | 10-17 transformers | 18-19 im2col producers
+#include <stdio.h>
+
 #include <algorithm>
 
 #include "ptx.cuh"
@@ -31,7 +33,7 @@ constexpr int kB0A1Stride = 4608;
 constexpr int kB0DsBytes = 16 * 256;        // downsample im2col tile: 128 rows x 32 B
 constexpr int kB0NA1 = 4, kB0ND1 = 6, kB0NDS = 2;
 constexpr int kB0Threads = 640;
-constexpr int kB0ZW = 392;                  // z columns staged per strip: 3*j0-4 .. 3*j0+387
+constexpr int kB0ZW = 400;                  // z columns kept per row: 3*j0-4 .. 3*j0+395 (392 used)
 constexpr int kB0W2Bytes = 6 * 32 * 128;    // conv2 weight image (6 taps x [32 rows x 128 B])
 constexpr int kB0ImgBytes = kB0W2Bytes + 2 * 1024 + 6 * 1024;   // + B1, B1' + 3 x (Bds, Bds')
 
@@ -42,6 +44,7 @@ struct Block0Params {
   const float* b1;         // [32] conv1 bias (bn2 folded)
   const float* b2;         // [32] conv2 bias + downsample bias
   int B, W, J, Wo, Jn, n_jt, n_slots;
+  long long* stats;        // optional: per-CTA MMA-warp wait cycles [total, a1full, d1empty, vfull, tempty, dsfull]
 };
 
 __device__ __forceinline__ uint64_t b0_desc_noswz(uint32_t smem_addr) {   // LBO 128 B, SBO 256 B
@@ -81,8 +84,9 @@ block0_tc_kernel(const Block0Params p) {
   uint8_t* s_ring = smem + kB0ImgBytes;                        // v tiles
   uint8_t* s_a1 = s_ring + (size_t)p.n_slots * kB0Slab;        // conv1 im2col ring
   uint8_t* s_ds = s_a1 + kB0NA1 * kB0A1Stride;                 // downsample im2col ring
-  float* s_z = reinterpret_cast<float*>(s_ds + kB0NDS * kB0DsBytes);   // [23][kB0ZW] fp32 window of z
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_z + 23 * kB0ZW);
+  __half* s_zh = reinterpret_cast<__half*>(s_ds + kB0NDS * kB0DsBytes);   // [3][kB0ZW] rolling rows of z, hi halves
+  __half* s_zl = s_zh + 3 * kB0ZW;                                        // ... lo halves
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_zl + 3 * kB0ZW);
   uint64_t* full = bars;                   // [8]  v tile written (8 transformer warps)
   uint64_t* empty = bars + 8;              // [8]  v tile consumed (tcgen05.commit)
   uint64_t* tfull = bars + 16;             // [2]  conv2 accumulators complete
@@ -132,12 +136,14 @@ block0_tc_kernel(const Block0Params p) {
     int slot = 0;
     uint32_t phase = 0;
     int nstart = 0, nds = 0;
+    long long w_a1 = 0, w_d1 = 0, w_vf = 0, w_te = 0, w_ds = 0;
+    const long long t_begin = clock64();
 
     auto issue_conv1_row = [&]() {         // the three phase tiles of one v row
       for (int phi = 0; phi < 3; ++phi, ++n1) {
         const int ka = n1 % kB0NA1, kd = n1 % kB0ND1;
-        mbar_wait(&a1full[ka], (n1 / kB0NA1) & 1);
-        mbar_wait(&d1empty[kd], ((n1 / kB0ND1) & 1) ^ 1);
+        { long long c0 = clock64(); mbar_wait(&a1full[ka], (n1 / kB0NA1) & 1); w_a1 += clock64() - c0; }
+        { long long c0 = clock64(); mbar_wait(&d1empty[kd], ((n1 / kB0ND1) & 1) ^ 1); w_d1 += clock64() - c0; }
         tc_fence_after_sync();
         if (leader) {
           const uint64_t a = b0_desc_noswz(a1_base + (uint32_t)(ka * kB0A1Stride));
@@ -195,7 +201,7 @@ block0_tc_kernel(const Block0Params p) {
           for (int i = 0; i < 3; ++i) { sl[i] = s2; ph[i] = p2; advance(s2, p2); }
         }
         for (int phi = 0; phi < 3; ++phi) {                      // pass 1: dh=1 completes output row r-1
-          mbar_wait(&full[sl[phi]], ph[phi]);
+          { long long c0 = clock64(); mbar_wait(&full[sl[phi]], ph[phi]); w_vf += clock64() - c0; }
           tc_fence_after_sync();
           if (has_o1 && leader) issue_group(sl[phi], 1, phi, buf_open, false);
           __syncwarp();
@@ -206,7 +212,7 @@ block0_tc_kernel(const Block0Params p) {
         }
         if (has_o0) {                                            // pass 2: dh=0 starts output row r
           buf_open = nstart & 1;
-          mbar_wait(&tempty[buf_open], ((nstart >> 1) & 1) ^ 1);
+          { long long c0 = clock64(); mbar_wait(&tempty[buf_open], ((nstart >> 1) & 1) ^ 1); w_te += clock64() - c0; }
           tc_fence_after_sync();
           ++nstart;
           for (int phi = 0; phi < 3; ++phi) {
@@ -218,16 +224,13 @@ block0_tc_kernel(const Block0Params p) {
           }
           // conv_downsample of z row r into the same accumulators (K = 16 im2col chunk, one B per pool phase)
           const int kq = nds % kB0NDS;
-          mbar_wait(&dsfull[kq], (nds / kB0NDS) & 1);
+          { long long c0 = clock64(); mbar_wait(&dsfull[kq], (nds / kB0NDS) & 1); w_ds += clock64() - c0; }
           tc_fence_after_sync();
           if (leader) {
             const uint64_t a = b0_desc_noswz(ds_base + (uint32_t)(kq * kB0DsBytes));
-#pragma unroll
-            for (int s = 0; s < 3; ++s) {
-              const uint32_t d_tmem = tmem_base + (uint32_t)((buf_open * 3 + s) * 32);
-              umma_f16(d_tmem, a, b0_desc_noswz(bds_addr + (uint32_t)(2 * s) * 1024), IDESC, 1);
-              umma_f16(d_tmem, a, b0_desc_noswz(bds_addr + (uint32_t)(2 * s + 1) * 1024), IDESC, 1);
-            }
+            const uint32_t d_tmem = tmem_base + (uint32_t)(buf_open * 96);      // columns [s0 | s1 | s2]
+            umma_f16(d_tmem, a, b0_desc_noswz(bds_addr), umma_idesc_f16(128, 96), 1);          // z_hi*w_hi + z_lo*w_hi
+            umma_f16(d_tmem, a, b0_desc_noswz(bds_addr + 3 * 1024), umma_idesc_f16(128, 96), 1);  // z_hi*w_lo
             umma_commit(&dsempty[kq]);
           }
           __syncwarp();
@@ -240,6 +243,10 @@ block0_tc_kernel(const Block0Params p) {
         }
         for (int i = 0; i < 3; ++i) advance(slot, phase);
       }
+    }
+    if (p.stats && leader) {
+      long long* st = p.stats + (size_t)blockIdx.x * 8;
+      st[0] = clock64() - t_begin; st[1] = w_a1; st[2] = w_d1; st[3] = w_vf; st[4] = w_te; st[5] = w_ds;
     }
   } else if (warp >= 2 && warp < 10) {
     // ======================================= epilogue =========================================
@@ -351,47 +358,56 @@ block0_tc_kernel(const Block0Params p) {
     // ============ im2col producers (warps 0, 18, 19): z taps as fp16 pairs, one 32-byte row per tile row ============
     const int ptid = warp == 0 ? lane : threadIdx.x - 17 * 32;   // 0..95
     int n = 0, nds = 0;
-    auto split1 = [](float v, __half& h, __half& l) {
-      v = fminf(fmaxf(v, -65504.f), 65504.f);
-      h = __float2half_rn(v);
-      l = __float2half_rn(v - __half2float(h));
-    };
+    constexpr int PER = (kB0ZW + 95) / 96;                       // z columns per producer thread (5)
     for (int t = blockIdx.x; t < n_strips; t += gridDim.x) {
       const int jt = t % p.n_jt, b = t / p.n_jt;
       const int j0 = jt * kB0Strip;
       const float* zb = p.z + (size_t)b * 23 * p.W;
-      // stage the strip's window of z (columns wz0 .. wz0+kB0ZW) once, asynchronously (4-byte cp.async:
-      // rows of z are not 16-byte aligned), zero outside [0,W)
-      const int wz0 = 3 * j0 - 4;
-      asm volatile("bar.sync 3, 96;" ::: "memory");            // all producer warps are done with the old window
-      for (int i = ptid; i < 23 * kB0ZW; i += 96) {
-        const int row = i / kB0ZW, w = wz0 + i % kB0ZW;
-        if (w >= 0 && w < p.W) {
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(s_z + i)),
-                       "l"(zb + (size_t)row * p.W + w)
-                       : "memory");
-        } else {
-          s_z[i] = 0.f;
+      const int wz0 = 3 * j0 - 4;                                // global column of window column 0
+      // z row `row` (0..22) -> registers (prefetch), then -> fp16 pairs in the rolling window slot row % 3
+      float pre[PER];
+      auto fetch_row = [&](int row) {
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+          const int c = ptid + 96 * q, w = wz0 + c;
+          pre[q] = (row >= 0 && row < 23 && c < kB0ZW && w >= 0 && w < p.W) ? __ldg(zb + (size_t)row * p.W + w) : 0.f;
         }
-      }
-      asm volatile("cp.async.wait_all;" ::: "memory");
-      asm volatile("bar.sync 3, 96;" ::: "memory");
-      auto zat = [&](int row, int w) -> float {                  // z[row][w] with conv zero padding
-        if (row < 0 || row > 22) return 0.f;
-        const int c = min(max(w - wz0, 0), kB0ZW - 1);           // clamp only matters for discarded tile rows
-        return s_z[row * kB0ZW + c];
       };
-      auto conv1_tile = [&](int r, int phi) {
+      auto store_row = [&](int row) {
+        __half* dh = s_zh + ((row + 3) % 3) * kB0ZW;
+        __half* dl = s_zl + ((row + 3) % 3) * kB0ZW;
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+          const int c = ptid + 96 * q;
+          if (c < kB0ZW) {
+            const float v = fminf(fmaxf(pre[q], -65504.f), 65504.f);
+            const __half hh = __float2half_rn(v);
+            dh[c] = hh;
+            dl[c] = __float2half_rn(v - __half2float(hh));
+          }
+        }
+      };
+      // three consecutive halves starting at column c of a window row -> (h0,h1) word and (h2,0)
+      auto conv1_tile = [&](int r, int phi) {                    // v row r: z rows r-1, r (zero outside 0..22)
         const int ka = n % kB0NA1;
         mbar_wait(&a1empty[ka], ((n / kB0NA1) & 1) ^ 1);
         uint8_t* dst = s_a1 + ka * kB0A1Stride;
+        const bool up = r >= 1 && r <= 23, dn = r <= 22;
+        const __half* uh = s_zh + ((r - 1 + 3) % 3) * kB0ZW;
+        const __half* ul = s_zl + ((r - 1 + 3) % 3) * kB0ZW;
+        const __half* nh = s_zh + (r % 3) * kB0ZW;
+        const __half* nl = s_zl + (r % 3) * kB0ZW;
+        const __half zero = __ushort_as_half((unsigned short)0);
         for (int jj = ptid; jj < 136; jj += 96) {
-          const int pos = 3 * (j0 - 1 + jj) + phi;
+          const int c = min(3 * jj + phi, kB0ZW - 3);            // clamp only matters for discarded rows >= 128
           __half h[6], l[6];
 #pragma unroll
-          for (int dh = 0; dh < 2; ++dh)
-#pragma unroll
-            for (int dw = 0; dw < 3; ++dw) split1(zat(r + dh - 1, pos + dw - 1), h[dh * 3 + dw], l[dh * 3 + dw]);
+          for (int dw = 0; dw < 3; ++dw) {
+            h[dw] = up ? uh[c + dw] : zero;
+            l[dw] = up ? ul[c + dw] : zero;
+            h[3 + dw] = dn ? nh[c + dw] : zero;
+            l[3 + dw] = dn ? nl[c + dw] : zero;
+          }
           uint8_t* row = dst + (jj >> 3) * 256 + (jj & 7) * 16;
           *reinterpret_cast<uint4*>(row) =
               make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(l[0], l[1]));
@@ -402,15 +418,17 @@ block0_tc_kernel(const Block0Params p) {
         if (lane == 0) mbar_arrive(&a1full[ka]);
         ++n;
       };
-      auto ds_tile = [&](int h) {
+      auto ds_tile = [&](int h) {                                // output row h: z row h, taps 3j-1 .. 3j+3
         const int kq = nds % kB0NDS;
         mbar_wait(&dsempty[kq], ((nds / kB0NDS) & 1) ^ 1);
         uint8_t* dst = s_ds + kq * kB0DsBytes;
+        const __half* zh = s_zh + (h % 3) * kB0ZW;
+        const __half* zl = s_zl + (h % 3) * kB0ZW;
         for (int m = ptid; m < 128; m += 96) {
-          const int w0 = 3 * (j0 + m) - 1;                         // taps 3j-1 .. 3j+3
+          const int c = 3 * m + 3;                               // window column of position 3*(j0+m) - 1
           __half hh[5], ll[5];
 #pragma unroll
-          for (int i = 0; i < 5; ++i) split1(zat(h, w0 + i), hh[i], ll[i]);
+          for (int i = 0; i < 5; ++i) { hh[i] = zh[c + i]; ll[i] = zl[c + i]; }
           uint8_t* row = dst + (m >> 3) * 256 + (m & 7) * 16;
           *reinterpret_cast<uint4*>(row) = make_uint4(pack_h2(hh[0], hh[1]), pack_h2(hh[2], hh[3]),
                                                       pack_h2(hh[4], ll[0]), pack_h2(ll[1], ll[2]));
@@ -421,8 +439,19 @@ block0_tc_kernel(const Block0Params p) {
         if (lane == 0) mbar_arrive(&dsfull[kq]);
         ++nds;
       };
+      // same order as the MMA warp consumes: a1(row 0); then per r: a1(row r+1), ds(row r)
+      asm volatile("bar.sync 3, 96;" ::: "memory");              // previous strip's window no longer read
+      fetch_row(0);
+      store_row(0);
+      fetch_row(1);
+      asm volatile("bar.sync 3, 96;" ::: "memory");
       for (int phi = 0; phi < 3; ++phi) conv1_tile(0, phi);
-      for (int r = 0; r < 24; ++r) {                             // same order as the MMA warp consumes
+      for (int r = 0; r < 24; ++r) {
+        if (r < 22) {                                            // z row r+1 into the window, prefetch r+2
+          store_row(r + 1);
+          fetch_row(r + 2);
+          asm volatile("bar.sync 3, 96;" ::: "memory");
+        }
         if (r < 23)
           for (int phi = 0; phi < 3; ++phi) conv1_tile(r + 1, phi);
         if (r <= 22) ds_tile(r);
@@ -465,9 +494,9 @@ void block0_pack_small(std::vector<uint8_t>& img, const std::vector<float>& w1 /
     for (int s = 0; s < 3; ++s)
       for (int dw = 0; dw < 3; ++dw) {
         const float w = wd[dw * 32 + o];
-        put_k16(img, bds + (size_t)(2 * s) * 1024, o, s + dw, w, false);
-        put_k16(img, bds + (size_t)(2 * s) * 1024, o, 5 + s + dw, w, false);
-        put_k16(img, bds + (size_t)(2 * s + 1) * 1024, o, s + dw, w, true);
+        put_k16(img, bds + (size_t)s * 1024, o, s + dw, w, false);          // rows 32*s + o of the hi-pattern block
+        put_k16(img, bds + (size_t)s * 1024, o, 5 + s + dw, w, false);
+        put_k16(img, bds + (size_t)(3 + s) * 1024, o, s + dw, w, true);     // lo-pattern block
       }
   }
 }
@@ -481,7 +510,7 @@ int launch_block0_tc(aasist_handle* h, int sm_count, const uint8_t* wimg, const 
   p.z = z; p.out = out; p.wimg = wimg; p.b1 = b1; p.b2 = b2;
   p.B = nb; p.W = W; p.J = (W + 2) / 3; p.Wo = W / 3; p.Jn = (p.Wo + 2) / 3;
   p.n_jt = (std::max(p.J, 3 * p.Jn) + kB0Strip - 1) / kB0Strip;
-  const int fixed = 1024 + kB0ImgBytes + kB0NA1 * kB0A1Stride + kB0NDS * kB0DsBytes + 23 * kB0ZW * 4 + 512;
+  const int fixed = 1024 + kB0ImgBytes + kB0NA1 * kB0A1Stride + kB0NDS * kB0DsBytes + 6 * kB0ZW * 2 + 512;
   p.n_slots = std::min(8, (227 * 1024 - fixed) / kB0Slab);
   if (p.n_slots < 6) {
     set_error("block0_tc: shared memory budget allows only %d ring slots", p.n_slots);
@@ -490,11 +519,31 @@ int launch_block0_tc(aasist_handle* h, int sm_count, const uint8_t* wimg, const 
   const size_t smem = (size_t)fixed + (size_t)p.n_slots * kB0Slab;
   AASIST_CUDA(cudaFuncSetAttribute(block0_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = std::min(nb * p.n_jt, sm_count);
+  static int want_stats = -1;
+  if (want_stats < 0) { const char* e = getenv("AASIST_B0_STATS"); want_stats = e ? atoi(e) : 0; }
+  p.stats = nullptr;
+  if (want_stats) {
+    AASIST_CUDA(cudaMalloc(&p.stats, sizeof(long long) * 8 * grid));
+    AASIST_CUDA(cudaMemset(p.stats, 0, sizeof(long long) * 8 * grid));
+  }
   {
     LaunchSpan span(h, "enc0.fused_conv1_conv2_tc", st);
     block0_tc_kernel<<<grid, kB0Threads, smem, st>>>(p);
   }
   AASIST_CUDA(cudaGetLastError());
+  if (want_stats) {   // debugging aid: where the MMA warp waits (cycles, mean over CTAs)
+    std::vector<long long> hst((size_t)8 * grid);
+    AASIST_CUDA(cudaStreamSynchronize(st));
+    AASIST_CUDA(cudaMemcpy(hst.data(), p.stats, sizeof(long long) * hst.size(), cudaMemcpyDeviceToHost));
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int c = 0; c < grid; ++c)
+      for (int k = 0; k < 6; ++k) acc[k] += (double)hst[(size_t)c * 8 + k] / grid;
+    const double rows = (double)nb * p.n_jt * 23 / grid;
+    fprintf(stderr, "[block0 stats] per row-tile cycles: total %.0f | wait a1full %.0f d1empty %.0f vfull %.0f tempty %.0f "
+            "dsfull %.0f | issuing %.0f\n", acc[0] / rows, acc[1] / rows, acc[2] / rows, acc[3] / rows, acc[4] / rows,
+            acc[5] / rows, (acc[0] - acc[1] - acc[2] - acc[3] - acc[4] - acc[5]) / rows);
+    cudaFree(p.stats);
+  }
   return 0;
 }
 
