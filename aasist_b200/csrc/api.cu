@@ -465,7 +465,12 @@ int aasist_destroy(aasist_handle* h) {
   for (auto e : h->prof_pool) cudaEventDestroy(e);
   if (h->pin_x) cudaFreeHost(h->pin_x);
   if (h->pin_out) cudaFreeHost(h->pin_out);
+  if (h->copy_stream) {
+    cudaStreamDestroy(h->copy_stream);
+    cudaEventDestroy(h->copy_done[0]); cudaEventDestroy(h->copy_done[1]); cudaEventDestroy(h->start_ev);
+  }
   cudaFree(h->dev_stage);
+  cudaFree(h->stage_meta);
   delete h;
   return AASIST_OK;
 }
@@ -702,10 +707,28 @@ int aasist_forward_host(aasist_handle* h, const float* x_host, int32_t B, int32_
     memcpy(h->pin_x, x_host, xb);
     src = h->pin_x;
   }
-  AASIST_CUDA(cudaMemcpyAsync(dx, src, xb, cudaMemcpyHostToDevice, st));
+  // chunked pipeline: the H2D copy of chunk c+1 (copy stream) overlaps the forward of chunk c
+  if (!h->copy_stream) {
+    AASIST_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) AASIST_CUDA(cudaEventCreateWithFlags(&h->copy_done[i], cudaEventDisableTiming));
+    AASIST_CUDA(cudaEventCreateWithFlags(&h->start_ev, cudaEventDisableTiming));
+  }
+  const int chunk = 128;
   float* d_lh = dout;
   float* d_lg = dout + (size_t)B * hd;
-  if ((rc = aasist_forward(h, dx, B, L, d_lh, d_lg, nullptr, nullptr, dws, ws_bytes, stream))) return rc;
+  AASIST_CUDA(cudaEventRecord(h->start_ev, st));                 // staging buffers are free once prior work is done
+  AASIST_CUDA(cudaStreamWaitEvent(h->copy_stream, h->start_ev, 0));
+  int nchunks = (B + chunk - 1) / chunk;
+  for (int c = 0; c < nchunks; ++c) {
+    const int b0 = c * chunk, nb = std::min(chunk, B - b0);
+    AASIST_CUDA(cudaMemcpyAsync(dx + (size_t)b0 * L, src + (size_t)b0 * L, sizeof(float) * (size_t)nb * L,
+                                cudaMemcpyHostToDevice, h->copy_stream));
+    AASIST_CUDA(cudaEventRecord(h->copy_done[c & 1], h->copy_stream));
+    AASIST_CUDA(cudaStreamWaitEvent(st, h->copy_done[c & 1], 0));
+    if ((rc = aasist_forward(h, dx + (size_t)b0 * L, nb, L, d_lh + (size_t)b0 * hd, d_lg + (size_t)b0 * 2, nullptr,
+                             nullptr, dws, ws_bytes, stream)))
+      return rc;
+  }
   AASIST_CUDA(cudaMemcpyAsync(h->pin_out, dout, ob, cudaMemcpyDeviceToHost, st));
   AASIST_CUDA(cudaStreamSynchronize(st));
   if (last_hidden_host) memcpy(last_hidden_host, h->pin_out, sizeof(float) * (size_t)B * hd);

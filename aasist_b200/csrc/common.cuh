@@ -142,6 +142,9 @@ struct aasist_handle {
   float* pin_x = nullptr; size_t pin_x_bytes = 0;
   float* pin_out = nullptr; size_t pin_out_bytes = 0;
   void* dev_stage = nullptr; size_t dev_stage_bytes = 0;
+  void* stage_meta = nullptr; size_t stage_meta_bytes = 0;   // offsets/lengths of aasist_pad_batch
+  cudaStream_t copy_stream = nullptr;     // H2D of chunk c+1 overlaps the forward of chunk c
+  cudaEvent_t copy_done[2] = {nullptr, nullptr}, start_ev = nullptr;
 };
 
 namespace aasist {

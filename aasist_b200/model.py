@@ -151,8 +151,25 @@ class _NativeModel(nn.Module):
         return cfg
 
     # -- parameter hand-over ---------------------------------------------------------------------
+    # parameters are handed to the library once and re-packed only when they change: `_apply`
+    # (.to/.cuda/.float) and `load_state_dict` mark the handle stale, in-place edits are caught by the
+    # tensors' version counters (a few microseconds per forward).
+    def _apply(self, fn, *args, **kwargs):
+        self._stale = True
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self._stale = True
+        return super().load_state_dict(*args, **kwargs)
+
     def _state_key(self):
-        return tuple((k, v.data_ptr(), v._version, str(v.device)) for k, v in self.state_dict().items())
+        tensors = self.__dict__.get("_flat")
+        if tensors is None or self.__dict__.get("_stale", True):
+            tensors = [v for _, v in self.state_dict(keep_vars=True).items()]
+            self.__dict__["_flat"] = tensors
+            self.__dict__["_stale"] = False
+            self.__dict__["_flat_id"] = self.__dict__.get("_flat_id", 0) + 1
+        return (self.__dict__["_flat_id"], sum(t._version for t in tensors))
 
     def _ensure_handle(self, device: torch.device):
         lib = _lib.load()
@@ -258,6 +275,31 @@ class _NativeModel(nn.Module):
             _lib.check(lib.aasist_forward_host(self._handle, x_host.data_ptr(), B, L,
                                                last_hidden.data_ptr(), output.data_ptr(), stream))
         return last_hidden, output
+
+    # -- input staging (reference data_utils.py:45-52 `pad`, applied per utterance at :208) -----------
+    def pad_batch(self, utterances, max_len: int = 64600) -> Tensor:
+        """Ragged 1-D waveforms -> (B, max_len) on the model's device by repeat-tiling / cropping,
+        in one kernel (the reference does this on the host, one utterance at a time)."""
+        lib = _lib.load()
+        dev = next(self.parameters()).device
+        self._ensure_handle(dev)
+        lengths = [int(u.numel()) for u in utterances]
+        if any(n < 1 for n in lengths):
+            raise ZeroDivisionError("empty utterance (reference `pad` divides by the length)")
+        flat = torch.cat([u.reshape(-1).to(device=dev, dtype=torch.float32, non_blocking=True) for u in utterances])
+        B = len(lengths)
+        offs = (C.c_int64 * B)()
+        lens = (C.c_int32 * B)()
+        acc = 0
+        for i, n in enumerate(lengths):
+            offs[i], lens[i] = acc, n
+            acc += n
+        out = torch.empty(B, max_len, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(lib.aasist_pad_batch(self._handle, flat.data_ptr(), offs, lens, B, max_len,
+                                            out.data_ptr(), stream))
+        return out
 
     def profile(self, enable: bool = True) -> None:
         """Bracket every kernel launch with CUDA events on the launching stream."""

@@ -35,6 +35,9 @@ def parse():
     ap.add_argument("--model", default="AASIST", choices=["AASIST", "AASIST-L", "RawGAT-ST"])
     ap.add_argument("--batch", type=int, default=512)
     ap.add_argument("--precision", default=None, help="fp32 | f16x3 (default: package default)")
+    ap.add_argument("--workload", default="batch", choices=["batch", "evalset"],
+                    help="batch: BASELINE configs[1] (default, the contract line); evalset: configs[2], one pass over "
+                         "71,237 synthetic utterances sharded across the ranks with one score all-gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -150,6 +153,55 @@ class ClockSampler:
         return out
 
 
+def run_evalset(args, model, dev, world, rank):
+    """BASELINE configs[2]: eval-set-sized scoring (71,237 utterances = ASVspoof2019-LA eval count), contiguous
+    block shards, local batches of 512, ONE all-gather of the scores.  Utterances are generated on device in
+    fixed chunks of 512 seeded 1234 + chunk_id, so the content does not depend on the world size."""
+    import torch
+    import torch.distributed as dist
+    from aasist_b200.scoring import score_utterances
+    n_total, chunk = 71237, 512
+
+    def source(start, stop):
+        parts = []
+        for cid in range(start // chunk, (stop - 1) // chunk + 1):
+            g = torch.Generator(device=dev).manual_seed(1234 + cid)
+            xc = 0.05 * torch.randn(chunk, L_SAMPLES, device=dev, generator=g)
+            lo, hi = max(start, cid * chunk), min(stop, (cid + 1) * chunk)
+            parts.append(xc[lo - cid * chunk:hi - cid * chunk])
+        return torch.cat(parts) if len(parts) > 1 else parts[0]
+
+    with torch.no_grad():
+        score_utterances(model, source, 4 * chunk * world, batch_size=chunk)        # warm-up
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        launches0 = model.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        scores = score_utterances(model, source, n_total, batch_size=chunk)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ms = float(t.item())
+        print(json.dumps({
+            "metric": "AASIST utterances/sec (4 s, 64600 samples)", "value": n_total / (ms * 1e-3), "unit": "utt/s",
+            "n_gpus": world, "steps": 1, "warmup": 1, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f16x3(split)+f32acc" if model.precision != "fp32" else "f32",
+            "data": "synthetic",
+            "config": {"workload": f"{args.model} eval-set-sized scoring: {n_total} utterances, L={L_SAMPLES}, contiguous "
+                                   f"block shards over {world} GPU(s), local batch {chunk}, one all-gather of scores; "
+                                   "waveform generation on device is inside the timed region",
+                       "n_utterances": n_total, "precision": model.precision},
+            "gpu_launches": int(model.launch_count() - launches0),
+            "scores_checksum": float(scores.double().sum().item()), "scores_head": scores[:4].tolist()}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_native(args):
     import torch
     import torch.distributed as dist
@@ -182,6 +234,9 @@ def run_native(args):
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     x = 0.05 * torch.randn(B, L_SAMPLES, device=dev, generator=g)
     gathered = torch.empty(world * B, device=dev) if world > 1 else None
+
+    if args.workload == "evalset":
+        return run_evalset(args, model, dev, world, rank)
 
     def step():
         _, out = model(x)

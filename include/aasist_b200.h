@@ -120,6 +120,15 @@ int aasist_forward(aasist_handle* h, const float* x, int32_t B, int32_t L,
 int aasist_forward_host(aasist_handle* h, const float* x_host, int32_t B, int32_t L,
                         float* last_hidden_host, float* logits_host, void* stream);
 
+/* ---- input staging (the step before the path) ------------------------------------------------ */
+/* Replaces the host-side `pad` (data_utils.py:45-52, used for every evaluation utterance at :208):
+ * B ragged utterances, already in device memory as one concatenated fp32 buffer, become the
+ * (B, max_len) model input: out[b][i] = x_b[i mod len_b] (repeat-tile; crop when len_b >= max_len).
+ * `offsets_host[b]` is the element offset of utterance b in `samples_dev`, `lengths_host[b]` its
+ * length (>= 1; an empty utterance is an error like the reference's ZeroDivisionError). */
+int aasist_pad_batch(aasist_handle* h, const float* samples_dev, const int64_t* offsets_host,
+                     const int32_t* lengths_host, int32_t B, int32_t max_len, float* out_dev, void* stream);
+
 /* ---- per-stage entry points (parity tests; same kernels as aasist_forward) -------------- */
 /* Device copy of the sinc filter bank, (n_filters, taps) fp32, into `bank_dev`. */
 int aasist_get_filterbank(aasist_handle* h, float* bank_dev, int32_t* n_filters, int32_t* taps);

@@ -342,6 +342,15 @@ def speech_like(n_utt: int, length: int, seed: int) -> Tensor:
     return torch.from_numpy(out)
 
 
+def pad(x: np.ndarray, max_len: int = 64600) -> np.ndarray:
+    """Repeat-tile / crop one utterance to max_len samples (data_utils.py:45-52)."""
+    x_len = x.shape[0]
+    if x_len >= max_len:                                              # :47-48
+        return x[:max_len]
+    num_repeats = int(max_len / x_len) + 1                            # :50
+    return np.tile(x, num_repeats)[:max_len]                          # :51 (tile of the 1-D signal)
+
+
 def n_params(sd: dict) -> int:
     """Trainable parameter count of a state_dict (excludes BN running stats)."""
     return sum(v.numel() for k, v in sd.items()

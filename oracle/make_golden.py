@@ -142,7 +142,37 @@ def pack(taps, x, bank, pools, enc_prefixes):
     return out
 
 
+def reference_pad():
+    """The reference's own `pad` (data_utils.py:45-52).  data_utils imports soundfile, which is not
+    installed, so the function is compiled from its source in place instead of importing the module."""
+    import ast
+    src = open(f"{REF}/data_utils.py").read()
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "pad"][0]
+    ns = {"np": np}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), f"{REF}/data_utils.py", "exec"), ns)
+    return ns["pad"]
+
+
+PAD_CASES = [(7, 101), (1000, 102), (21533, 103), (64599, 104), (64600, 105), (64601, 106), (100000, 107)]
+
+
+def make_pad_golden():
+    pad = reference_pad()
+    out = {}
+    for n, seed in PAD_CASES:
+        x = O.white_noise(1, n, seed)[0].numpy()
+        y = np.asarray(pad(x, 64600), dtype=np.float32)
+        assert y.shape == (64600,)
+        out[f"len{n}.sample"] = y[::499]
+        out[f"len{n}.tail"] = y[-16:]
+        out[f"len{n}.sum"] = np.array(y.astype(np.float64).sum())
+    np.savez_compressed(os.path.join(GOLD, "pad.npz"), **out)
+    print("pad golden written")
+
+
 def main():
+    if "--only-pad" in sys.argv:
+        return make_pad_golden()
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 8)
     cases = [
@@ -181,6 +211,7 @@ def main():
                                          "numpy": np.__version__}))
         np.savez_compressed(os.path.join(GOLD, f"RawGAT-ST_{tag}.npz"), **d)
         print("RawGAT-ST", tag, "logits[0] =", taps["output"][0].tolist())
+    make_pad_golden()
     json.dump(summary, open(os.path.join(GOLD, "summary.json"), "w"), indent=1)
     print(summary)
 

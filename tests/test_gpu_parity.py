@@ -182,3 +182,41 @@ def test_scoring_loop_matches_oracle_scores():
     ref = g.oracle_taps("AASIST-L", x)["output"][:, 1]
     assert scores.shape == (7,)
     assert (scores.cpu() - ref).abs().max().item() <= LOGIT_TOL
+
+
+def test_pad_batch_matches_reference_pad_bit_exactly():
+    g = _g()
+    import os
+    from oracle.make_golden import PAD_CASES
+    from tests.util import GOLD
+    gold = np.load(os.path.join(GOLD, "pad.npz"))
+    m = g.native_model("AASIST-L")
+    utts = [O.white_noise(1, n, seed)[0] for n, seed in PAD_CASES]
+    out = m.pad_batch(utts, 64600).cpu().numpy()
+    assert out.shape == (len(PAD_CASES), 64600)
+    for i, (n, seed) in enumerate(PAD_CASES):
+        assert np.array_equal(out[i], O.pad(utts[i].numpy(), 64600))          # byte work: bit-exact
+        assert np.array_equal(out[i][::499], gold[f"len{n}.sample"])
+        assert np.array_equal(out[i][-16:], gold[f"len{n}.tail"])
+    assert np.array_equal(m.pad_batch([utts[1].to(g.DEV)], 1234).cpu().numpy()[0], O.pad(utts[1].numpy(), 1234))
+    with pytest.raises(ZeroDivisionError):                                      # reference: int(max_len / 0)
+        m.pad_batch([torch.zeros(0)], 64600)
+
+
+def test_parameter_updates_are_picked_up():
+    g = _g()
+    import aasist_b200
+    from tests.util import load_sd
+    m = aasist_b200.Model(aasist_b200.CONFIGS["AASIST-L"], precision="fp32")
+    m.load_state_dict(load_sd("AASIST-L"))
+    m = m.to(g.DEV).eval()
+    x = O.speech_like(2, 64600, 31).to(g.DEV)
+    out0 = m(x)[1].clone()
+    assert torch.equal(m(x)[1], out0)
+    with torch.no_grad():
+        m.out_layer.bias.add_(1.0)                       # in-place edit -> version counter -> re-pack
+    out1 = m(x)[1]
+    assert torch.allclose(out1, out0 + 1.0, atol=1e-6)
+    sd = load_sd("AASIST-L")
+    m.load_state_dict(sd)                                # reload -> back to the original logits
+    assert torch.equal(m(x)[1], out0)

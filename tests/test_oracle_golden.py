@@ -71,3 +71,18 @@ def test_compare_topk_tie_policy():
     assert O.compare_topk(s, ref, torch.tensor([[0, 2]]))[0] == 0     # tie across the k boundary
     assert O.compare_topk(s, ref, torch.tensor([[1, 0]]))[0] == 2     # strict order violated
     assert O.compare_topk(s, ref, torch.tensor([[0, 3]]))[0] == 1
+
+
+def test_pad_oracle_matches_reference_pad():
+    # fixtures produced by the reference's own `pad` (data_utils.py:45-52), see oracle/make_golden.py
+    import os
+    from oracle.make_golden import PAD_CASES
+    from tests.util import GOLD
+    g = np.load(os.path.join(GOLD, "pad.npz"))
+    for n, seed in PAD_CASES:
+        x = O.white_noise(1, n, seed)[0].numpy()
+        y = O.pad(x, 64600)
+        assert y.shape == (64600,) and y.dtype == np.float32
+        assert np.array_equal(y[::499], g[f"len{n}.sample"])
+        assert np.array_equal(y[-16:], g[f"len{n}.tail"])
+        assert y.astype(np.float64).sum() == float(g[f"len{n}.sum"])
