@@ -92,7 +92,7 @@ def run_reference(args):
         "e2e": {"value": mean, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -187,7 +187,7 @@ def run_evalset(args, model, dev, world, rank):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
         ms = float(t.item())
-        print(json.dumps({
+        _emit({
             "metric": "AASIST utterances/sec (4 s, 64600 samples)", "value": n_total / (ms * 1e-3), "unit": "utt/s",
             "n_gpus": world, "steps": 1, "warmup": 1, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f16x3(split)+f32acc" if model.precision != "fp32" else "f32",
@@ -197,7 +197,7 @@ def run_evalset(args, model, dev, world, rank):
                                    "waveform generation on device is inside the timed region",
                        "n_utterances": n_total, "precision": model.precision},
             "gpu_launches": int(model.launch_count() - launches0),
-            "scores_checksum": float(scores.double().sum().item()), "scores_head": scores[:4].tolist()}))
+            "scores_checksum": float(scores.double().sum().item()), "scores_head": scores[:4].tolist()})
     if world > 1:
         dist.destroy_process_group()
 
@@ -214,7 +214,10 @@ def run_native(args):
     if args.gpus > 1 and world == 1:
         raise SystemExit("for --gpus N>1 launch with: python -m torch.distributed.run --nnodes=1 "
                          "--nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...")
-    os.environ["NCCL_DEBUG"] = os.environ.get("AASIST_NCCL_DEBUG", "WARN")   # keep stdout to ONE json line
+    if "AASIST_NCCL_DEBUG" in os.environ:
+        os.environ["NCCL_DEBUG"] = os.environ["AASIST_NCCL_DEBUG"]
+    else:
+        os.environ.pop("NCCL_DEBUG", None)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -364,10 +367,19 @@ def run_native(args):
         line["cpu_baseline"] = {"value": best, "unit": "utt/s", "cores": cores, "kind": "port",
                                 "sample": f"{n_cpu} utterances, best of 2 after 1 warm-up, torch CPU fp32, "
                                           f"{cores} threads (oracle/aasist_oracle.py)"}
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
+
+def _emit(obj) -> None:
+    """The contract is ONE json line on stdout; native libraries (NCCL prints its version) write to fd 1
+    directly, so fd 1 is pointed at stderr for the whole run and the result goes to the saved descriptor."""
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
 
 if __name__ == "__main__":
     a = parse()
