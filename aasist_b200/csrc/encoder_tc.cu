@@ -12,10 +12,13 @@
 // loaded once and feeds three accumulators.  Zero padding (conv pad (1,1)/(0,1)) is TMA
 // out-of-bounds fill; positions >= W are kept zero in memory by every producer.
 //
-// Kernel structure (persistent, 1 CTA/SM, 192 threads): warp 0 = TMA producer, warp 1 = TMEM
-// allocator + single-thread tcgen05.mma issuer, warps 2-5 = epilogue (tcgen05.ld -> bias /
-// SELU / residual / max-pool -> hi/lo split -> 128-byte vector stores).  smem ring of input
-// tiles (full/empty mbarriers), double-buffered accumulators (tmem_full/tmem_empty mbarriers).
+// Kernel structure (persistent, 1 CTA/SM, 320 threads): warp 0 = TMA producer, warp 1 = TMEM
+// allocator + MMA issuer (warp-uniform schedule, one elected lane issues tcgen05.mma/commit),
+// warps 2-9 = epilogue (two warps per TMEM lane quadrant; batched tcgen05.ld -> bias / SELU /
+// residual / max-pool -> fp16-pair split -> vector stores).  smem ring of input tiles (full/empty
+// mbarriers), double-buffered accumulators (tmem_full/tmem_empty mbarriers).
+// This file serves the blocks that change the channel count (conv_downsample) and the 64-channel
+// blocks; block 0 lives in block0_tc.cu and the 32->32 identity blocks in block_fused_tc.cu.
 #include <algorithm>
 
 #include "ptx.cuh"
@@ -31,13 +34,13 @@ constexpr int kSlabBytes = 17 * 1024;       // 130 rows x 128 B, rounded up to t
 constexpr int kEpiWarps = 8;                // two warps per TMEM lane quadrant (column halves)
 constexpr int kTcThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxSlots = 8;
-static int tc_chunk() {                     // utterances per encoder pass (bounds scratch: ~95 MB each)
+static int tc_chunk() {                     // utterances per encoder pass (bounds scratch: ~60 MB each)
   static int v = -1;
-  if (v < 0) { const char* e = getenv("AASIST_TC_CHUNK"); v = e ? std::max(1, atoi(e)) : 128; }
+  if (v < 0) { const char* e = getenv("AASIST_TC_CHUNK"); v = e ? std::max(1, atoi(e)) : 256; }
   return v;
 }
 
-enum { TC_CONV1 = 0, TC_CONV2_ID = 1, TC_CONV2_DS = 2, TC_CONV2_Z = 3 };
+enum { TC_CONV1 = 0, TC_CONV2_ID = 1, TC_CONV2_DS = 2 };
 
 struct ConvTcParams {
   int B, H_out, J, n_jt, W_in, Co, Wo, Jn;
@@ -47,10 +50,6 @@ struct ConvTcParams {
   __half* out;             // CONV1: [B][24][3][J][2*COP]; CONV2: [B][23][3][Jn][2*COP]
   float* out_f32;          // last block: (B,Co,23,Wo) fp32 NCHW (then `out` is unused)
   const __half* idn;       // CONV2_ID: block input, [B][23][3][J][2*COP]
-  const float* z;          // CONV2_Z: block-0 input (B,23,W_in) fp32
-  const float* wd;         // CONV2_Z: conv_downsample weights [3][COP] fp32
-  const float* w1;         // CONV2_Z: block-0 conv1 weights (bn2 folded) [6][32] fp32
-  const float* b1;         // CONV2_Z: block-0 conv1 bias (bn2 folded) [32]
   const uint8_t* wimg;     // pre-swizzled weight image (shared-memory layout)
   int wimg_bytes;
 };
@@ -64,9 +63,7 @@ struct BlockTc {
   int ci = 0, co = 0, cpi = 0, cop = 0;
   bool downsample = false;
   ConvTc c1, c2;
-  float* w1_f32 = nullptr;   // block 0 only: conv1 (bn2 folded) [6][32] fp32
-  float* wd_f32 = nullptr;   // block 0 only: conv_downsample [3][32] fp32
-  std::vector<float> w1_host, wd_host;
+  std::vector<float> w1_host, wd_host;   // block 0 only: conv1 (bn2 folded) [6][32], conv_downsample [3][32]
   uint8_t* b0_img = nullptr; // block 0 only: conv2 + conv1/downsample K=16 operand images (block0_tc.cu)
 };
 struct TcState {
@@ -166,17 +163,12 @@ __device__ __forceinline__ void add_pair16(const Pair16& p, float (&v)[16]) {
 // all phases -> completes an output row and hands it to the epilogue; then dh=0 -> starts the
 // next one), which gives the epilogue half a row of slack to drain the buffer being recycled.
 //
-// MODE TC_CONV2_Z (encoder block 0) has no TMA at all: its A operand v = selu(bn2(conv1(z)))
-// is COMPUTED by 8 producer warps from the fp32 front-end output z (1 input channel, K = 6:
-// not GEMM-shaped) and written as swizzled fp16 hi/lo tiles straight into the ring, so the
-// 66 MB/utterance intermediate never touches HBM.
+// Encoder block 0 and the 32 -> 32 identity blocks do not use this kernel: their conv1 -> conv2
+// intermediate stays on chip (block0_tc.cu, block_fused_tc.cu).
 // ------------------------------------------------------------------------------------------
-constexpr int kProdWarps = 8;
-constexpr int kZW = 3 * (kTileJ + 2) + 2;     // z columns a strip needs: 3*130 positions + 1 halo each side
-
 template <int MODE>
 struct ConvCfg {
-  static constexpr int kThreads = kTcThreads + (MODE == TC_CONV2_Z ? 32 * kProdWarps : 0);
+  static constexpr int kThreads = kTcThreads;
 };
 
 template <int CPI, int COP, int MODE>
@@ -190,7 +182,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr int SIDE_TAP_BYTES = COP * 128;          // side input is 32 channels wide (1 slab)
   constexpr int TMEM_COLS = (6 * COP <= 256) ? 256 : 512;
   constexpr uint32_t IDESC = umma_idesc_f16(128, COP);
-  constexpr bool FUSED = MODE == TC_CONV2_Z;
   constexpr bool HAS_SIDE = MODE == TC_CONV2_DS;
   constexpr int NCH = COP / 32;                      // 16-column chunks per epilogue warp (it owns COP/2 columns)
   constexpr int R_IN = (MODE == TC_CONV1) ? 23 : 24; // input rows walked per strip
@@ -206,9 +197,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull = bars + 2 * kMaxSlots;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* s_f32 = reinterpret_cast<float*>(bars + 2 * kMaxSlots + 6);   // FUSED: wd[3][32] then z strip
-  float* s_wd = s_f32;
-  float* s_z = s_f32 + 96;                                             // [23][kZW]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_strips = p.B * p.n_jt;
@@ -217,12 +205,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // weights: global image -> shared (generic proxy), then make visible to the async proxy
   for (int i = threadIdx.x; i < p.wimg_bytes / 16; i += NTHREADS)
     reinterpret_cast<uint4*>(s_w)[i] = __ldg(reinterpret_cast<const uint4*>(p.wimg) + i);
-  if (FUSED)
-    for (int i = threadIdx.x; i < 96; i += NTHREADS) s_wd[i] = __ldg(p.wd + i);
   fence_proxy_async_smem();
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.n_slots; ++i) {
-      mbar_init(&full[i], FUSED ? kProdWarps : 1);
+      mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -230,7 +216,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&tempty[i], kEpiWarps);   // one arrival per epilogue warp
     }
     fence_barrier_init();
-    if (!FUSED) prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmA);
     if (HAS_SIDE) prefetch_tensormap(&tmS);
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_ptr);
@@ -241,7 +227,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
-    if (!FUSED && lane == 0) {
+    if (lane == 0) {
       int slot = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < n_strips; t += gridDim.x) {
@@ -468,7 +454,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         } else {
           // operands that do not depend on the accumulators are fetched before waiting for them
           Pair16 idn[(MODE == TC_CONV2_ID) ? 3 : 1][NCH];
-          float zq[5];
           if (MODE == TC_CONV2_ID) {
 #pragma unroll
             for (int s = 0; s < 3; ++s)
@@ -481,13 +466,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   idn[s][c] = zero_pair16();
                 }
               }
-          } else if (MODE == TC_CONV2_Z) {
-            const float* zr = p.z + ((size_t)b * 23 + h) * p.W_in;
-#pragma unroll
-            for (int i = 0; i < 5; ++i) {
-              const int w = 3 * j - 1 + i;
-              zq[i] = (w >= 0 && w < p.W_in) ? __ldg(zr + w) : 0.f;
-            }
           }
           mbar_wait(&tfull[buf], (tcount >> 1) & 1);
           tc_fence_after_sync();
@@ -515,18 +493,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[s][c][i]);
               if (MODE == TC_CONV2_ID) {
                 add_pair16(idn[s][c], v);
-              } else if (MODE == TC_CONV2_Z) {
-                // conv_downsample (1 -> COP channels, k(1,3)) on CUDA cores; weights broadcast from smem
-#pragma unroll
-                for (int i4 = 0; i4 < 4; ++i4) {
-                  const float4 w0 = *reinterpret_cast<const float4*>(s_wd + col0 + c * 16 + 4 * i4);
-                  const float4 w1 = *reinterpret_cast<const float4*>(s_wd + 32 + col0 + c * 16 + 4 * i4);
-                  const float4 w2 = *reinterpret_cast<const float4*>(s_wd + 64 + col0 + c * 16 + 4 * i4);
-                  v[4 * i4 + 0] += w0.x * zq[s] + w1.x * zq[s + 1] + w2.x * zq[s + 2];
-                  v[4 * i4 + 1] += w0.y * zq[s] + w1.y * zq[s + 1] + w2.y * zq[s + 2];
-                  v[4 * i4 + 2] += w0.z * zq[s] + w1.z * zq[s + 1] + w2.z * zq[s + 2];
-                  v[4 * i4 + 3] += w0.w * zq[s] + w1.w * zq[s + 1] + w2.w * zq[s + 2];
-                }
               }
 #pragma unroll
               for (int i = 0; i < 16; ++i) m[i] = s == 0 ? v[i] : fmaxf(m[i], v[i]);
@@ -545,81 +511,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               store_pair16(o, o + COP, m);
             }
           }
-        }
-      }
-    }
-  } else if (FUSED) {
-    // ============ operand producers (warps 10..17): v = selu(bn2(conv1(z))) -> swizzled ring tiles ============
-    // thread (row jj in an 8-row group, channel octet cg): lane = cg*8 + (jj & 7) so that a
-    // quarter-warp writes eight different rows of the same 16-byte chunk column -> the XOR
-    // swizzle spreads them over all banks.
-    const int pw = warp - (2 + kEpiWarps);
-    const int ptid = threadIdx.x - 32 * (2 + kEpiWarps);
-    const int cg = lane >> 3, rr = lane & 7;
-    float w1[6][8], b1[8];
-#pragma unroll
-    for (int tp = 0; tp < 6; ++tp)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) w1[tp][i] = __ldg(p.w1 + tp * 32 + cg * 8 + i);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) b1[i] = __ldg(p.b1 + cg * 8 + i);
-    int slot = 0;
-    uint32_t phase = 0;
-    uint32_t gseq = 0;                    // running 8-row-group counter: balances groups over the warps
-    for (int t = blockIdx.x; t < n_strips; t += gridDim.x) {
-      const int jt = t % p.n_jt, b = t / p.n_jt;
-      const int jstart = jt * kTileJ - 1;
-      const int wz0 = 3 * jstart - 1;     // global column of s_z[.][0]
-      // producers-only barrier: everyone is done reading the previous strip's z
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * kProdWarps) : "memory");
-      for (int i = ptid; i < 23 * kZW; i += 32 * kProdWarps) {
-        const int row = i / kZW, col = i % kZW, w = wz0 + col;
-        s_z[i] = (w >= 0 && w < p.W_in) ? __ldg(p.z + ((size_t)b * 23 + row) * p.W_in + w) : 0.f;
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * kProdWarps) : "memory");
-      for (int r = 0; r < 24; ++r) {
-        const float* z_up = s_z + (r - 1) * kZW;   // conv1 tap dh=0 reads z row r-1 (zero pad outside 0..22)
-        const float* z_dn = s_z + r * kZW;         // tap dh=1 reads z row r
-        const bool up_ok = r >= 1, dn_ok = r <= 22;
-        for (int phi = 0; phi < 3; ++phi) {
-          mbar_wait(&empty[slot], phase ^ 1);
-          uint8_t* dst = s_ring + (size_t)slot * SLOT_BYTES;
-          // 17 eight-row groups per tile, dealt round-robin (running offset) to the producer warps
-          const int g_first = (int)((pw + kProdWarps - (gseq % kProdWarps)) % kProdWarps);
-          gseq += 17;
-          for (int g = g_first; g < 17; g += kProdWarps) {
-            const int jj = g * 8 + rr;             // tile row; 130..135 are never read by the MMAs
-            const int pos = 3 * (jstart + jj) + phi;
-            const int zi = 3 * jj + phi;           // s_z column of position pos-1
-            float v[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = b1[i];
-            float a[6];
-#pragma unroll
-            for (int dw = 0; dw < 3; ++dw) {
-              const int zc = min(zi + dw, kZW - 1);
-              a[dw] = up_ok ? z_up[zc] : 0.f;
-              a[3 + dw] = dn_ok ? z_dn[zc] : 0.f;
-            }
-#pragma unroll
-            for (int tp = 0; tp < 6; ++tp)
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = fmaf(a[tp], w1[tp][i], v[i]);
-            const bool valid = pos >= 0 && pos < p.W_in;   // conv2 zero-pads v itself
-            uint32_t hw[4], lw[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float x0 = valid ? selu_fast(v[2 * i]) : 0.f, x1 = valid ? selu_fast(v[2 * i + 1]) : 0.f;
-              split_pack2<true>(x0, x1, hw[i], lw[i]);
-            }
-            uint8_t* row = dst + jj * 128;
-            *reinterpret_cast<uint4*>(row + ((cg ^ rr) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            *reinterpret_cast<uint4*>(row + (((4 + cg) ^ rr) << 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-          }
-          fence_proxy_async_smem();          // generic-proxy stores -> visible to tcgen05 operand fetch
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&full[slot]);
-          if (++slot == p.n_slots) { slot = 0; phase ^= 1; }
         }
       }
     }
@@ -768,14 +659,12 @@ static int pack_block_tc(aasist_handle* h, const std::string& pfx, int index, Bl
     std::vector<float> w(6 * 32, 0.f), wd(3 * 32, 0.f);
     for (int o = 0; o < co; ++o)
       for (int t = 0; t < 6; ++t) w[t * 32 + o] = (float)((double)w1[(size_t)o * 6 + t] * sc[o]);
-    if ((rc = upload_f(&blk.w1_f32, w))) return rc;
     blk.w1_host = w;
     const auto &wdv = P(".conv_downsample.weight"), &bd = P(".conv_downsample.bias");
     for (int o = 0; o < co; ++o) {
       for (int t = 0; t < 3; ++t) wd[t * 32 + o] = wdv[(size_t)o * 3 + t];
       bias2[o] = (float)((double)b2[o] + (double)bd[o]);
     }
-    if ((rc = upload_f(&blk.wd_f32, wd))) return rc;
     blk.wd_host = wd;
   } else {
     const int tap_bytes = (blk.cpi / 32) * blk.cop * 128;
@@ -855,7 +744,7 @@ void tc_destroy(aasist_handle* h) {
     for (int i = 0; i < 6; ++i) {
       BlockTc& b = h->tc->blocks[e][i];
       cudaFree(b.c1.wimg); cudaFree(b.c1.bias); cudaFree(b.c2.wimg); cudaFree(b.c2.bias);
-      cudaFree(b.w1_f32); cudaFree(b.wd_f32); cudaFree(b.b0_img);
+      cudaFree(b.b0_img);
     }
   cudaFree(h->tc->front_bimg);
   delete h->tc;
@@ -873,10 +762,15 @@ static void make_tc_plan(const aasist_handle* h, int L, TcPlan& pl) {
   pl.z = sizeof(float) * (size_t)kSpecNodes * pl.W[0];
   pl.mid = pl.act = 0;
   for (int i = 0; i < 6; ++i) {
-    int cop = pad_ch(h->cfg.enc_channels[i][1]);
-    pl.mid = std::max(pl.mid, (size_t)24 * 3 * pl.J[i] * 2 * cop * 2);
+    const int ci = h->cfg.enc_channels[i][0], co = h->cfg.enc_channels[i][1];
+    const int cop = pad_ch(co);
+    // blocks whose conv1 -> conv2 intermediate stays on chip need no `mid` buffer:
+    // block 0 (block0_tc.cu) and 32->32 identity blocks (block_fused_tc.cu)
+    const bool fused = i == 0 || (ci == co && pad_ch(ci) == 32 && cop == 32);
+    if (!fused) pl.mid = std::max(pl.mid, (size_t)24 * 3 * pl.J[i] * 2 * cop * 2);
     pl.act = std::max(pl.act, (size_t)23 * 3 * pl.J[i + 1] * 2 * cop * 2);
   }
+  pl.mid = std::max<size_t>(pl.mid, 256);
 }
 static inline size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 
@@ -895,8 +789,7 @@ template <int CPI, int COP, int MODE>
 static int launch_conv(aasist_handle* h, const char* name, const CUtensorMap& tmA, const CUtensorMap& tmS,
                        ConvTcParams p, cudaStream_t st) {
   constexpr int SLOT = (CPI / 32) * kSlabBytes;
-  constexpr int EXTRA = (MODE == TC_CONV2_Z) ? (96 + 23 * kZW) * 4 : 0;   // wd + z strip (fused block 0)
-  const int budget = 227 * 1024 - 1024 /*align*/ - p.wimg_bytes - 256 /*barriers*/ - EXTRA;
+  const int budget = 227 * 1024 - 1024 /*align*/ - p.wimg_bytes - 256 /*barriers*/;
   int n_slots = std::min(kMaxSlots, budget / SLOT);
   if (n_slots < 2) {
     set_error("conv_tc: not enough shared memory for the input ring (weights %d bytes)", p.wimg_bytes);
@@ -910,7 +803,7 @@ static int launch_conv(aasist_handle* h, const char* name, const CUtensorMap& tm
     if (slots_override >= 2 && slots_override <= n_slots) n_slots = slots_override;
   }
   p.n_slots = n_slots;
-  size_t smem = 1024 + (size_t)p.wimg_bytes + (size_t)n_slots * SLOT + 256 + EXTRA;
+  size_t smem = 1024 + (size_t)p.wimg_bytes + (size_t)n_slots * SLOT + 256;
   auto kern = conv_tc_kernel<CPI, COP, MODE>;
   AASIST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int n_strips = p.B * p.n_jt;
@@ -941,13 +834,21 @@ static int run_block_tc(aasist_handle* h, int enc, int index, const __half* in_p
   memset(&tmMid, 0, sizeof(tmMid));
   if (index > 0 && (rc = make_act_tmap(h, &tmMid, mid, blk.cop, J, 24, nb))) return rc;
   if (index > 0 && (rc = make_act_tmap(h, &tmIn, in_pairs, blk.cpi, J, 23, nb))) return rc;
-  // ---- conv1 (block 0: fused into the conv2 kernel as its operand producer) ----
-  if (index > 0) {
+  // ---- block 0 and 32->32 identity blocks: the whole block is one kernel, intermediate kept on chip ----
+  if (index == 0)
+    return launch_block0_tc(h, h->tc->sm_count, blk.b0_img, blk.c1.bias, blk.c2.bias, z, nb, W, out_pairs, st);
+  if (!blk.downsample && blk.cpi == 32 && blk.cop == 32) {
+    static const char* names[6] = {"", "enc1.fused_tc", "enc2.fused_tc", "enc3.fused_tc", "enc4.fused_tc", "enc5.fused_tc"};
+    return launch_block_fused_tc(h, h->tc->sm_count, names[index], tmIn, blk.c1.wimg, blk.c2.wimg, blk.c1.bias,
+                                 blk.c2.bias, in_pairs, nb, W, blk.co, out_pairs, out_f32, st);
+  }
+  // ---- conv1 ----
+  {
     ConvTcParams p;
     memset(&p, 0, sizeof(p));
     p.B = nb; p.H_out = 24; p.J = J; p.n_jt = (J + kTileJ - 1) / kTileJ; p.W_in = W; p.Co = blk.co;
     p.bias = blk.c1.bias; p.out = mid; p.wimg = blk.c1.wimg; p.wimg_bytes = blk.c1.wimg_bytes;
-    if (blk.cpi == 32 && blk.cop == 32) rc = launch_conv<32, 32, TC_CONV1>(h, kConvNames[0][index], tmIn, tmIn, p, st);
+    if (blk.cpi == 32 && blk.cop == 32) rc = launch_conv<32, 32, TC_CONV1>(h, kConvNames[0][index], tmIn, tmIn, p, st);   // 32 -> 24 (AASIST-L)
     else if (blk.cpi == 32 && blk.cop == 64) rc = launch_conv<32, 64, TC_CONV1>(h, kConvNames[0][index], tmIn, tmIn, p, st);
     else if (blk.cpi == 64 && blk.cop == 64) rc = launch_conv<64, 64, TC_CONV1>(h, kConvNames[0][index], tmIn, tmIn, p, st);
     else { set_error("f16x3 path: unsupported conv1 shape %d->%d", blk.ci, blk.co); rc = AASIST_E_INVALID; }
@@ -960,17 +861,9 @@ static int run_block_tc(aasist_handle* h, int enc, int index, const __half* in_p
   p.B = nb; p.H_out = 23; p.J = J; p.W_in = W; p.Co = blk.co; p.Wo = Wo; p.Jn = Jn;
   p.n_jt = (std::max(J, std::min(3 * Jn, Wo + 2)) + kTileJ - 1) / kTileJ;
   p.bias = blk.c2.bias; p.out = out_pairs; p.out_f32 = out_f32; p.wimg = blk.c2.wimg; p.wimg_bytes = blk.c2.wimg_bytes;
-  if (index == 0) {
-    static int old_b0 = -1;   // AASIST_TC_BLOCK0_CUDA=1: previous variant (conv1 + downsample on CUDA cores)
-    if (old_b0 < 0) { const char* e = getenv("AASIST_TC_BLOCK0_CUDA"); old_b0 = e ? atoi(e) : 0; }
-    if (!old_b0 && !out_f32)
-      return launch_block0_tc(h, h->tc->sm_count, blk.b0_img, blk.c1.bias, blk.c2.bias, z, nb, W, out_pairs, st);
-    p.z = z; p.wd = blk.wd_f32; p.w1 = blk.w1_f32; p.b1 = blk.c1.bias;
-    rc = launch_conv<32, 32, TC_CONV2_Z>(h, "enc0.fused_conv1_conv2_tc", tmIn, tmIn, p, st);
-  } else if (!blk.downsample) {
-    p.idn = in_pairs;
-    if (blk.cop == 32) rc = launch_conv<32, 32, TC_CONV2_ID>(h, kConvNames[1][index], tmMid, tmMid, p, st);
-    else rc = launch_conv<64, 64, TC_CONV2_ID>(h, kConvNames[1][index], tmMid, tmMid, p, st);
+  if (!blk.downsample) {
+    p.idn = in_pairs;   // 64 -> 64 identity block (the 32 -> 32 ones took the fused path above)
+    rc = launch_conv<64, 64, TC_CONV2_ID>(h, kConvNames[1][index], tmMid, tmMid, p, st);
   } else {
     if (blk.cop == 32) rc = launch_conv<32, 32, TC_CONV2_DS>(h, kConvNames[1][index], tmMid, tmIn, p, st);
     else rc = launch_conv<64, 64, TC_CONV2_DS>(h, kConvNames[1][index], tmMid, tmIn, p, st);

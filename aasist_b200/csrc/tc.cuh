@@ -1,5 +1,6 @@
 // Tensor-core (tcgen05, fp16 hi/lo split x3) path: entry points used by api.cu.
 #pragma once
+#include <cuda.h>
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -24,4 +25,8 @@ int block0_image_bytes();
 int block0_w2_bytes();
 int launch_block0_tc(aasist_handle* h, int sm_count, const uint8_t* wimg, const float* b1, const float* b2,
                      const float* z, int nb, int W, __half* out, cudaStream_t st);
+// 32->32 residual block with identity shortcut, conv1 -> conv2 fused on chip (block_fused_tc.cu)
+int launch_block_fused_tc(aasist_handle* h, int sm_count, const char* name, const CUtensorMap& tmX,
+                          const uint8_t* w1img, const uint8_t* w2img, const float* b1, const float* b2,
+                          const __half* x, int nb, int W, int Co, __half* out, float* out_f32, cudaStream_t st);
 }  // namespace aasist

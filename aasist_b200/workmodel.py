@@ -29,7 +29,7 @@ def kernel_flops(name: str, kernel: str, batch: int, length: int = 64600) -> flo
     m = stage_macs(name, length)
     if kernel.startswith("enc") and "." in kernel:          # "enc{i}.conv1[_tc]" / "enc{i}.conv2[_tc]"
         blk, conv = kernel.split(".")[0], kernel.split(".")[1]
-        if conv.startswith("fused"):
+        if conv.startswith("fused"):   # whole block in one kernel
             macs = m[f"{blk}.conv1"] + m[f"{blk}.conv2"] + m[f"{blk}.ds"]
         else:
             macs = m[f"{blk}.conv1"] if conv.startswith("conv1") else m[f"{blk}.conv2"] + m[f"{blk}.ds"]
