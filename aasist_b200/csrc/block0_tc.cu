@@ -287,12 +287,8 @@ block0_tc_kernel(const Block0Params p) {
           b0_split2<false>(x0, x1, hw[i], lw[i]);
         }
         __half* o = p.out + ((((size_t)b * 23 + h) * 3 + (j % 3)) * p.Jn + j / 3) * 64 + col0;
-        uint4* oh = reinterpret_cast<uint4*>(o);
-        uint4* ol = reinterpret_cast<uint4*>(o + 32);
-        oh[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-        oh[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
-        ol[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-        ol[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+        st_global_256(o, hw);
+        st_global_256(o + 32, lw);
       }
     }
   } else if (warp >= 10 && warp < 18) {

@@ -324,12 +324,8 @@ block_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const BlockFusedP
 #pragma unroll
           for (int i = 0; i < 8; ++i) bf_split2<false>(mx[2 * i], mx[2 * i + 1], hw[i], lw[i]);
           __half* o = p.out + ((((size_t)b * 23 + h) * 3 + (j % 3)) * p.Jn + j / 3) * 64 + col0;
-          uint4* oh = reinterpret_cast<uint4*>(o);
-          uint4* ol = reinterpret_cast<uint4*>(o + 32);
-          oh[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-          oh[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
-          ol[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-          ol[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+          st_global_256(o, hw);
+          st_global_256(o + 32, lw);
         }
       }
     }

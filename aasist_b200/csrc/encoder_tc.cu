@@ -19,7 +19,10 @@
 // mbarriers), double-buffered accumulators (tmem_full/tmem_empty mbarriers).
 // This file serves the blocks that change the channel count (conv_downsample) and the 64-channel
 // blocks; block 0 lives in block0_tc.cu and the 32->32 identity blocks in block_fused_tc.cu.
+#include <stdio.h>
+
 #include <algorithm>
+#include <vector>
 
 #include "ptx.cuh"
 #include "tc.cuh"
@@ -31,8 +34,7 @@ using namespace ptx;
 constexpr int kTileJ = 128;                 // pooled columns per CTA tile (UMMA M)
 constexpr int kBoxRows = kTileJ + 2;        // rows j0-1 .. j0+128
 constexpr int kSlabBytes = 17 * 1024;       // 130 rows x 128 B, rounded up to the 1024-B swizzle atom
-constexpr int kEpiWarps = 8;                // two warps per TMEM lane quadrant (column halves)
-constexpr int kTcThreads = 64 + 32 * kEpiWarps;
+// epilogue warps: every warp owns 16 accumulator columns of one TMEM lane quadrant (COP/16 warps per quadrant)
 constexpr int kMaxSlots = 8;
 static int tc_chunk() {                     // utterances per encoder pass (bounds scratch: ~60 MB each)
   static int v = -1;
@@ -52,6 +54,7 @@ struct ConvTcParams {
   const __half* idn;       // CONV2_ID: block input, [B][23][3][J][2*COP]
   const uint8_t* wimg;     // pre-swizzled weight image (shared-memory layout)
   int wimg_bytes;
+  long long* stats;        // optional: MMA-warp wait cycles per CTA [total, full(TMA), tempty(epilogue)]
 };
 
 struct ConvTc {            // one convolution's packed device state
@@ -108,12 +111,8 @@ __device__ __forceinline__ void store_pair16(__half* hi_dst, __half* lo_dst, con
   uint32_t hw[8], lw[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) split_pack2<LOWER_BOUNDED>(v[2 * i], v[2 * i + 1], hw[i], lw[i]);
-  uint4* hd = reinterpret_cast<uint4*>(hi_dst);
-  uint4* ld = reinterpret_cast<uint4*>(lo_dst);
-  hd[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-  hd[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
-  ld[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-  ld[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+  st_global_256(hi_dst, hw);
+  st_global_256(lo_dst, lw);
 }
 __device__ __forceinline__ void store_pair32(__half* hi_dst, __half* lo_dst, const float (&v)[32]) {
   float a[16], b[16];
@@ -125,10 +124,11 @@ __device__ __forceinline__ void store_pair32(__half* hi_dst, __half* lo_dst, con
 struct Pair16 { uint4 h[2], l[2]; };   // 16 channels of an activation: hi and lo fp16 vectors
 __device__ __forceinline__ Pair16 load_pair16(const __half* hi_src, const __half* lo_src) {
   Pair16 p;
-  p.h[0] = __ldg(reinterpret_cast<const uint4*>(hi_src));
-  p.h[1] = __ldg(reinterpret_cast<const uint4*>(hi_src) + 1);
-  p.l[0] = __ldg(reinterpret_cast<const uint4*>(lo_src));
-  p.l[1] = __ldg(reinterpret_cast<const uint4*>(lo_src) + 1);
+  uint32_t a[8], b[8];
+  ld_global_nc_256(hi_src, a);
+  ld_global_nc_256(lo_src, b);
+  p.h[0] = make_uint4(a[0], a[1], a[2], a[3]); p.h[1] = make_uint4(a[4], a[5], a[6], a[7]);
+  p.l[0] = make_uint4(b[0], b[1], b[2], b[3]); p.l[1] = make_uint4(b[4], b[5], b[6], b[7]);
   return p;
 }
 __device__ __forceinline__ Pair16 zero_pair16() {
@@ -166,13 +166,14 @@ __device__ __forceinline__ void add_pair16(const Pair16& p, float (&v)[16]) {
 // Encoder block 0 and the 32 -> 32 identity blocks do not use this kernel: their conv1 -> conv2
 // intermediate stays on chip (block0_tc.cu, block_fused_tc.cu).
 // ------------------------------------------------------------------------------------------
-template <int MODE>
+template <int COP>
 struct ConvCfg {
-  static constexpr int kThreads = kTcThreads;
+  static constexpr int kEpiWarps = COP / 4;                 // 8 (COP = 32) or 16 (COP = 64)
+  static constexpr int kThreads = 64 + 32 * kEpiWarps;
 };
 
 template <int CPI, int COP, int MODE>
-__global__ void __launch_bounds__(ConvCfg<MODE>::kThreads, 1)
+__global__ void __launch_bounds__(ConvCfg<COP>::kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmS,
                const ConvTcParams p) {
   constexpr int SLABS = CPI / 32;                    // 128-byte-wide K slabs per input tile
@@ -183,9 +184,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr int TMEM_COLS = (6 * COP <= 256) ? 256 : 512;
   constexpr uint32_t IDESC = umma_idesc_f16(128, COP);
   constexpr bool HAS_SIDE = MODE == TC_CONV2_DS;
-  constexpr int NCH = COP / 32;                      // 16-column chunks per epilogue warp (it owns COP/2 columns)
+  constexpr int NCH = 1;                             // 16-column chunks per epilogue warp
+  constexpr int kEpiWarps = ConvCfg<COP>::kEpiWarps;
   constexpr int R_IN = (MODE == TC_CONV1) ? 23 : 24; // input rows walked per strip
-  constexpr int NTHREADS = ConvCfg<MODE>::kThreads;
+  constexpr int NTHREADS = ConvCfg<COP>::kThreads;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -263,6 +265,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t w_base = smem_u32(s_w);
     const uint32_t ring_base = smem_u32(s_ring);
     const bool leader = elect_one();
+    long long w_te = 0, w_fu = 0;
+    const long long t_begin = clock64();
 
     // All MMAs of one input tile (phase phi) for tap row dh into accumulator buffer `buf`.
     // Pool phase s is served by tap dw with (s + dw - 1) == phi (mod 3), from A rows shifted by
@@ -311,7 +315,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     };
     auto begin_row = [&]() -> int {       // claim the next accumulator buffer (waits for its drain)
       const int buf = nstart & 1;
-      mbar_wait(&tempty[buf], ((nstart >> 1) & 1) ^ 1);
+      { long long c0 = clock64(); mbar_wait(&tempty[buf], ((nstart >> 1) & 1) ^ 1); w_te += clock64() - c0; }
       tc_fence_after_sync();
       ++nstart;
       return buf;
@@ -335,7 +339,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (two_pass) {
           if (o1_fresh) buf_open = begin_row();
           for (int phi = 0; phi < 3; ++phi) {
-            mbar_wait(&full[sl[phi]], ph[phi]);
+            { long long c0 = clock64(); mbar_wait(&full[sl[phi]], ph[phi]); w_fu += clock64() - c0; }
             tc_fence_after_sync();
             if (has_o1 && leader) issue_group(sl[phi], 1, phi, buf_open, o1_fresh && phi == 0, false);
             __syncwarp();
@@ -363,7 +367,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           int buf_new = -1;
           if (o1_fresh) buf_open = begin_row();
           for (int phi = 0; phi < 3; ++phi) {
-            mbar_wait(&full[sl[phi]], ph[phi]);
+            { long long c0 = clock64(); mbar_wait(&full[sl[phi]], ph[phi]); w_fu += clock64() - c0; }
             tc_fence_after_sync();
             if (has_o1 && leader) issue_group(sl[phi], 1, phi, buf_open, o1_fresh && phi == 0, false);
             __syncwarp();
@@ -383,7 +387,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int i = 0; i < 3; ++i) advance(slot, phase);
         if (HAS_SIDE && has_o0) {
           for (int phi = 0; phi < 3; ++phi) {
-            mbar_wait(&full[slot], phase);
+            { long long c0 = clock64(); mbar_wait(&full[slot], phase); w_fu += clock64() - c0; }
             tc_fence_after_sync();
             if (leader) {
               issue_group(slot, 0, phi, buf_open, false, true);
@@ -399,13 +403,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+    if (p.stats && leader) {
+      long long* stt = p.stats + (size_t)blockIdx.x * 4;
+      stt[0] = clock64() - t_begin; stt[1] = w_fu; stt[2] = w_te;
+    }
   } else if (warp < 2 + kEpiWarps) {
     // =============================== epilogue (warps 2..9) ========================
     // warp -> (TMEM lane quadrant, column half): thread = one pooled column j, COP/2 channels
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int part = (warp - 2) >> 2;                 // which 16-column slice of the accumulators
     const int r = quad * 32 + lane;
-    const int col0 = half * (COP / 2);
+    const int col0 = part * 16;
     float bias[NCH][16];
 #pragma unroll
     for (int c = 0; c < NCH; ++c)
@@ -808,11 +816,31 @@ static int launch_conv(aasist_handle* h, const char* name, const CUtensorMap& tm
   AASIST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int n_strips = p.B * p.n_jt;
   const int grid = std::min(n_strips, h->tc->sm_count);
+  static int want_stats = -1;
+  if (want_stats < 0) { const char* e = getenv("AASIST_TC_STATS"); want_stats = e ? atoi(e) : 0; }
+  p.stats = nullptr;
+  if (want_stats) {
+    AASIST_CUDA(cudaMalloc(&p.stats, sizeof(long long) * 4 * grid));
+    AASIST_CUDA(cudaMemset(p.stats, 0, sizeof(long long) * 4 * grid));
+  }
   {
     LaunchSpan span(h, name, st);
-    kern<<<grid, ConvCfg<MODE>::kThreads, smem, st>>>(tmA, tmS, p);
+    kern<<<grid, ConvCfg<COP>::kThreads, smem, st>>>(tmA, tmS, p);
   }
   AASIST_CUDA(cudaGetLastError());
+  if (want_stats) {   // debugging aid: where the MMA warp waits (cycles per output row-tile, mean over CTAs)
+    std::vector<long long> hst((size_t)4 * grid);
+    AASIST_CUDA(cudaStreamSynchronize(st));
+    AASIST_CUDA(cudaMemcpy(hst.data(), p.stats, sizeof(long long) * hst.size(), cudaMemcpyDeviceToHost));
+    double acc[3] = {0, 0, 0};
+    for (int c = 0; c < grid; ++c)
+      for (int k = 0; k < 3; ++k) acc[k] += (double)hst[(size_t)c * 4 + k] / grid;
+    const double rows = (double)n_strips * p.H_out / grid;
+    fprintf(stderr, "[%s stats] per row-tile cycles: total %.0f | wait full(TMA) %.0f tempty(epilogue) %.0f | issuing %.0f"
+            " | slots %d strips/CTA %.2f\n", name, acc[0] / rows, acc[1] / rows, acc[2] / rows,
+            (acc[0] - acc[1] - acc[2]) / rows, p.n_slots, (double)n_strips / grid);
+    cudaFree(p.stats);
+  }
   return 0;
 }
 

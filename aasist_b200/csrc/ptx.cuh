@@ -190,6 +190,20 @@ __device__ __forceinline__ bool elect_one() {
 
 }  // namespace ptx
 
+// 256-bit global store / load (sm_100: STG.256 / LDG.256): one full 32-byte sector per lane per
+// instruction -- the epilogues write with thread = row, so every lane hits a different 128-byte line
+// and the number of L1 wavefronts is what bounds them
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t (&w)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+               "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_nc_256(const void* p, uint32_t (&w)[8]) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+               : "l"(p));
+}
+
 // fp32 -> (hi, lo) fp16 pair: hi = rn(v), lo = rn(v - hi); v ~= hi + lo to ~2^-22 relative
 __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
   hi = __float2half_rn(v);
