@@ -268,18 +268,6 @@ block_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const BlockFusedP
       for (int h = 0; h < 23; ++h, ++tcount) {
         const int buf = tcount & 1;
         const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 96 + col0);
-        // identity operand x[b][h][s][j][col0..col0+16): fetched before waiting for the accumulators
-        uint4 ih[3][2], il[3][2];
-#pragma unroll
-        for (int s = 0; s < 3; ++s) {
-          if (live && j < p.J) {
-            const uint4* xs = reinterpret_cast<const uint4*>(p.x + ((((size_t)b * 23 + h) * 3 + s) * p.J + j) * 64 + col0);
-            ih[s][0] = __ldg(xs); ih[s][1] = __ldg(xs + 1);
-            il[s][0] = __ldg(xs + 4); il[s][1] = __ldg(xs + 5);     // lo half-row starts 32 halves = 64 B later
-          } else {
-            ih[s][0] = ih[s][1] = il[s][0] = il[s][1] = make_uint4(0, 0, 0, 0);
-          }
-        }
         mbar_wait(&tfull[buf], (tcount >> 1) & 1);
         tc_fence_after_sync();
         uint32_t acc[3][16];
@@ -294,20 +282,24 @@ block_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const BlockFusedP
         float mx[16];
 #pragma unroll
         for (int s = 0; s < 3; ++s) {
+          // identity operand x[b][h][s][j][col0..col0+16) (L2-resident: conv1 just read this row)
+          uint32_t ih[8], il[8];
+          if (j < p.J) {
+            const __half* xs = p.x + ((((size_t)b * 23 + h) * 3 + s) * p.J + j) * 64 + col0;
+            ld_global_nc_256(xs, ih);
+            ld_global_nc_256(xs + 32, il);                       // lo half-row: 32 halves = 64 B later
+          } else {
 #pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const uint32_t hw4[4] = {ih[s][q].x, ih[s][q].y, ih[s][q].z, ih[s][q].w};
-            const uint32_t lw4[4] = {il[s][q].x, il[s][q].y, il[s][q].z, il[s][q].w};
+            for (int k = 0; k < 8; ++k) ih[k] = il[k] = 0u;
+          }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float2 fa = __half22float2(*reinterpret_cast<const __half2*>(&hw4[k]));
-              const float2 fb = __half22float2(*reinterpret_cast<const __half2*>(&lw4[k]));
-              const int i = 8 * q + 2 * k;
-              const float v0 = __uint_as_float(acc[s][i]) + (fa.x + fb.x);
-              const float v1 = __uint_as_float(acc[s][i + 1]) + (fa.y + fb.y);
-              mx[i] = s == 0 ? v0 : fmaxf(mx[i], v0);
-              mx[i + 1] = s == 0 ? v1 : fmaxf(mx[i + 1], v1);
-            }
+          for (int k = 0; k < 8; ++k) {
+            const float2 fa = __half22float2(*reinterpret_cast<const __half2*>(&ih[k]));
+            const float2 fb = __half22float2(*reinterpret_cast<const __half2*>(&il[k]));
+            const float v0 = __uint_as_float(acc[s][2 * k]) + (fa.x + fb.x);
+            const float v1 = __uint_as_float(acc[s][2 * k + 1]) + (fa.y + fb.y);
+            mx[2 * k] = s == 0 ? v0 : fmaxf(mx[2 * k], v0);
+            mx[2 * k + 1] = s == 0 ? v1 : fmaxf(mx[2 * k + 1], v1);
           }
         }
 #pragma unroll

@@ -460,21 +460,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         } else {
-          // operands that do not depend on the accumulators are fetched before waiting for them
-          Pair16 idn[(MODE == TC_CONV2_ID) ? 3 : 1][NCH];
-          if (MODE == TC_CONV2_ID) {
-#pragma unroll
-            for (int s = 0; s < 3; ++s)
-#pragma unroll
-              for (int c = 0; c < NCH; ++c) {
-                if (j < p.J) {
-                  const __half* x = p.idn + ((((size_t)b * 23 + h) * 3 + s) * p.J + j) * (2 * COP) + col0 + c * 16;
-                  idn[s][c] = load_pair16(x, x + COP);
-                } else {
-                  idn[s][c] = zero_pair16();
-                }
-              }
-          }
           mbar_wait(&tfull[buf], (tcount >> 1) & 1);
           tc_fence_after_sync();
           const bool valid = j < p.Wo;
@@ -500,7 +485,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[s][c][i]);
               if (MODE == TC_CONV2_ID) {
-                add_pair16(idn[s][c], v);
+                // identity operand of this pool phase (L2-resident: conv1 of this block just read it);
+                // loaded here rather than prefetched: 16 epilogue warps hide the latency and the
+                // kernel stays inside its 96-register budget
+                if (j < p.J) {
+                  const __half* x = p.idn + ((((size_t)b * 23 + h) * 3 + s) * p.J + j) * (2 * COP) + col0 + c * 16;
+                  add_pair16(load_pair16(x, x + COP), v);
+                }
               }
 #pragma unroll
               for (int i = 0; i < 16; ++i) m[i] = s == 0 ? v[i] : fmaxf(m[i], v[i]);
