@@ -18,7 +18,10 @@
 // i.e. SBO = 256 B (next 8-row group), LBO = 128 B (second 16-byte K half of a UMMA_K=16 chunk).
 // The A tile is a 9-slot ring indexed by K chunk: the MMA warp releases chunk kc of tile t
 // (tcgen05.commit) and the producers immediately rebuild it for tile t+1.
+#include <stdio.h>
+
 #include <algorithm>
+#include <vector>
 
 #include "ptx.cuh"
 #include "tc.cuh"
@@ -33,7 +36,7 @@ constexpr int kFtKC = 9;                      // K chunks of 16: 131 taps+phases
 constexpr int kFtAChunk = kFtTile * 32;       // bytes of one A K-chunk (hi or lo)
 constexpr int kFtBChunk = kFtN * 32;          // bytes of one B K-chunk (hi or lo)
 constexpr int kFtSeg = 3 * kFtTile + 16 * kFtKC;   // staged samples per tile (527 used)
-constexpr int kFtProdWarps = 4;               // 128 producer threads: one per A row
+constexpr int kFtProdWarps = 8;               // 256 producer threads: two per A row (even / odd K chunks)
 constexpr int kFtThreads = 64 + 32 * 8 + 32 * kFtProdWarps;
 constexpr int kFtBufCols = 256;               // TMEM column stride between the two accumulators
 constexpr float kFtScale = 1024.f;            // 2^10 on both operands
@@ -44,6 +47,7 @@ struct FrontTcParams {
   const uint8_t* bimg;     // filter operand image: [hi|lo][kc][208 rows x 32 B], no-swizzle canonical
   int B, L, Wp, n_tiles_per_utt;
   float bn_scale, bn_shift;
+  long long* stats;        // optional: MMA-warp wait cycles per CTA [total, afull(producers), tempty(epilogue)]
 };
 
 // no-swizzle K-major descriptor: LBO = 128 B, SBO = 256 B, version 1, layout 0
@@ -70,27 +74,51 @@ __device__ __forceinline__ void front_epilogue(uint32_t t_row, const FrontTcPara
                                                uint64_t* tempty_bar, int lane) {
   constexpr int COL0 = HALF == 0 ? 0 : 96;           // first loaded column (16-aligned)
   constexpr int FI0 = HALF == 0 ? 0 : 12, NFI = HALF == 0 ? 12 : 11;
-  uint32_t acc[7][16];
-#pragma unroll
-  for (int c = 0; c < 7; ++c) tmem_ld16_async(t_row + (uint32_t)(COL0 + 16 * c), acc[c]);
-#pragma unroll
-  for (int c = 0; c < 7; ++c) tmem_ld_wait16(acc[c]);
-  tc_fence_before_sync();
-  __syncwarp();
-  if (lane == 0) mbar_arrive(tempty_bar);
-  if (ti >= p.Wp) return;
+  // two batches of accumulator columns (4 + 3 chunks of 16) keep the register count low:
+  // batch 0 covers bands whose nine columns end before local column 64, batch 1 the rest
   float* o = p.out + ((size_t)b * kSpecNodes) * p.Wp + ti;
+  const bool live = ti < p.Wp;
+  constexpr int SPLIT = 7;                                       // bands 0..6 of this half live in columns < 63
+  {
+    uint32_t acc[4][16];
 #pragma unroll
-  for (int f = 0; f < NFI; ++f) {
-    float m = 0.f;
+    for (int c = 0; c < 4; ++c) tmem_ld16_async(t_row + (uint32_t)(COL0 + 16 * c), acc[c]);
 #pragma unroll
-    for (int q = 0; q < 9; ++q) {
-      const int col = 9 * (FI0 + f) + q - COL0;      // compile-time after unrolling
-      m = fmaxf(m, fabsf(__uint_as_float(acc[col >> 4][col & 15])));
+    for (int c = 0; c < 4; ++c) tmem_ld_wait16(acc[c]);
+#pragma unroll
+    for (int f = 0; f < NFI; ++f) {
+      const int c0 = 9 * (FI0 + f) - COL0;
+      if (c0 + 8 < 64) {                                         // compile-time after unrolling
+        float m = 0.f;
+#pragma unroll
+        for (int q = 0; q < 9; ++q) m = fmaxf(m, fabsf(__uint_as_float(acc[(c0 + q) >> 4][(c0 + q) & 15])));
+        m *= 1.f / (kFtScale * kFtScale);                        // undo the 2^10 operand scales (exact)
+        if (live) o[(size_t)(FI0 + f) * p.Wp] = ft_selu(fmaf(m, p.bn_scale, p.bn_shift));
+      }
     }
-    m *= 1.f / (kFtScale * kFtScale);                // undo the 2^10 operand scales (exact)
-    o[(size_t)(FI0 + f) * p.Wp] = ft_selu(fmaf(m, p.bn_scale, p.bn_shift));
   }
+  {
+    uint32_t acc[4][16];                                         // local columns 48 .. 111
+#pragma unroll
+    for (int c = 0; c < 4; ++c) tmem_ld16_async(t_row + (uint32_t)(COL0 + 48 + 16 * c), acc[c]);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) tmem_ld_wait16(acc[c]);
+    tc_fence_before_sync();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tempty_bar);
+#pragma unroll
+    for (int f = 0; f < NFI; ++f) {
+      const int c0 = 9 * (FI0 + f) - COL0;
+      if (c0 + 8 >= 64) {
+        float m = 0.f;
+#pragma unroll
+        for (int q = 0; q < 9; ++q) m = fmaxf(m, fabsf(__uint_as_float(acc[(c0 + q - 48) >> 4][(c0 + q - 48) & 15])));
+        m *= 1.f / (kFtScale * kFtScale);
+        if (live) o[(size_t)(FI0 + f) * p.Wp] = ft_selu(fmaf(m, p.bn_scale, p.bn_shift));
+      }
+    }
+  }
+  (void)SPLIT;
 }
 
 __global__ void __launch_bounds__(kFtThreads, 1)
@@ -120,7 +148,7 @@ sinc_frontend_tc_kernel(const FrontTcParams p) {
   fence_proxy_async_smem();
   if (threadIdx.x == 0) {
     for (int i = 0; i < kFtKC; ++i) {
-      mbar_init(&afull[i], kFtProdWarps);
+      mbar_init(&afull[i], kFtProdWarps / 2);      // the four warps that own this chunk
       mbar_init(&aempty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -141,13 +169,15 @@ sinc_frontend_tc_kernel(const FrontTcParams p) {
     const uint32_t a_base = smem_u32(s_a), b_base = smem_u32(s_b);
     constexpr uint32_t IDESC = umma_idesc_f16(128, kFtN);
     int tcount = 0;
+    long long w_te = 0, w_af = 0;
+    const long long t_begin = clock64();
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
       const int buf = tcount & 1;
-      mbar_wait(&tempty[buf], ((tcount >> 1) & 1) ^ 1);
+      { long long c0 = clock64(); mbar_wait(&tempty[buf], ((tcount >> 1) & 1) ^ 1); w_te += clock64() - c0; }
       tc_fence_after_sync();
       const uint32_t d = tmem_base + (uint32_t)(buf * kFtBufCols);
       for (int kc = 0; kc < kFtKC; ++kc) {
-        mbar_wait(&afull[kc], tcount & 1);
+        { long long c0 = clock64(); mbar_wait(&afull[kc], tcount & 1); w_af += clock64() - c0; }
         tc_fence_after_sync();
         if (leader) {
           const uint64_t a_hi = umma_desc_noswz(a_base + (uint32_t)((2 * kc) * kFtAChunk));
@@ -163,6 +193,10 @@ sinc_frontend_tc_kernel(const FrontTcParams p) {
       }
       if (leader) umma_commit(&tfull[buf]);
       __syncwarp();
+    }
+    if (p.stats && leader) {
+      long long* stt = p.stats + (size_t)blockIdx.x * 4;
+      stt[0] = clock64() - t_begin; stt[1] = w_af; stt[2] = w_te;
     }
   } else if (warp >= 2 && warp < 10) {
     // =============================== epilogue ====================================
@@ -180,31 +214,48 @@ sinc_frontend_tc_kernel(const FrontTcParams p) {
     }
   } else if (warp >= 10) {
     // ============ A-operand producers: stage the waveform segment, build the Hankel-like tile ============
-    const int ptid = threadIdx.x - 320;          // 0..127 == tile row
+    const int ptid = threadIdx.x - 320;          // 0..255: row = ptid & 127, K-chunk parity = ptid >> 7
+    const int prow = ptid & 127, ppart = ptid >> 7;
     int tcount = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
+    constexpr int PER = (kFtSeg + 1 + 32 * kFtProdWarps - 1) / (32 * kFtProdWarps);   // samples per thread (5)
+    float pre[PER];
+    // fetch the waveform segment of tile t into registers (issued one tile ahead: the global-load
+    // latency overlaps the construction of the previous tile)
+    auto fetch = [&](int t) {
       const int b = t / p.n_tiles_per_utt, tile = t % p.n_tiles_per_utt;
-      const size_t g0 = (size_t)3 * tile * kFtTile;     // first sample of the segment
+      const size_t g0 = (size_t)3 * tile * kFtTile;
       const float* xb = p.x + (size_t)b * p.L;
-      asm volatile("bar.sync 2, %0;" ::"n"(32 * kFtProdWarps) : "memory");   // previous tile fully built
-      for (int i = ptid; i < kFtSeg + 1; i += 32 * kFtProdWarps) {
+#pragma unroll
+      for (int q = 0; q < PER; ++q) {
+        const int i = ptid + 32 * kFtProdWarps * q;
         const size_t g = g0 + i;
-        const float v = g < (size_t)p.L ? __ldg(xb + g) * kFtScale : 0.f;
-        const float vc = fminf(fmaxf(v, -65504.f), 65504.f);
-        const __half h = __float2half_rn(vc);
-        const __half l = __float2half_rn(vc - __half2float(h));
-        xh0[i] = h;
-        xl0[i] = l;
-        if (i > 0) { xh1[i - 1] = h; xl1[i - 1] = l; }
+        pre[q] = (i < kFtSeg + 1 && g < (size_t)p.L) ? __ldg(xb + g) : 0.f;
+      }
+    };
+    if ((int)blockIdx.x < n_tiles) fetch(blockIdx.x);
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
+      asm volatile("bar.sync 2, %0;" ::"n"(32 * kFtProdWarps) : "memory");   // previous tile fully built
+#pragma unroll
+      for (int q = 0; q < PER; ++q) {
+        const int i = ptid + 32 * kFtProdWarps * q;
+        if (i < kFtSeg + 1) {
+          const float vc = fminf(fmaxf(pre[q] * kFtScale, -65504.f), 65504.f);
+          const __half h = __float2half_rn(vc);
+          const __half l = __float2half_rn(vc - __half2float(h));
+          xh0[i] = h;
+          xl0[i] = l;
+          if (i > 0) { xh1[i - 1] = h; xl1[i - 1] = l; }
+        }
       }
       asm volatile("bar.sync 2, %0;" ::"n"(32 * kFtProdWarps) : "memory");
+      if (t + (int)gridDim.x < n_tiles) fetch(t + gridDim.x);
       // row ptid, K halves [8q, 8q+8) = samples 3*ptid + 8q ...; pick the copy that makes the start even
-      const int start0 = 3 * ptid;
+      const int start0 = 3 * prow;
       const bool odd = start0 & 1;
       const uint32_t* srch = reinterpret_cast<const uint32_t*>(odd ? xh1 : xh0) + ((start0 - (odd ? 1 : 0)) >> 1);
       const uint32_t* srcl = reinterpret_cast<const uint32_t*>(odd ? xl1 : xl0) + ((start0 - (odd ? 1 : 0)) >> 1);
-      const uint32_t row_off = (uint32_t)((ptid >> 3) * 256 + (ptid & 7) * 16);
-      for (int kc = 0; kc < kFtKC; ++kc) {
+      const uint32_t row_off = (uint32_t)((prow >> 3) * 256 + (prow & 7) * 16);
+      for (int kc = ppart; kc < kFtKC; kc += 2) {
         mbar_wait(&aempty[kc], (tcount & 1) ^ 1);
         uint8_t* ah = s_a + (size_t)(2 * kc) * kFtAChunk + row_off;
         uint8_t* al = ah + kFtAChunk;
@@ -274,11 +325,30 @@ int launch_frontend_tc(aasist_handle* h, const uint8_t* bimg, int sm_count, cons
   const size_t smem = 1024 + 2 * kFtKC * kFtBChunk + 2 * kFtKC * kFtAChunk + 4 * (kFtSeg + 16) * 2 + 256;
   AASIST_CUDA(cudaFuncSetAttribute(sinc_frontend_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = std::min(B * p.n_tiles_per_utt, sm_count);
+  static int want_stats = -1;
+  if (want_stats < 0) { const char* e = getenv("AASIST_TC_STATS"); want_stats = e ? atoi(e) : 0; }
+  p.stats = nullptr;
+  if (want_stats) {
+    AASIST_CUDA(cudaMalloc(&p.stats, sizeof(long long) * 4 * grid));
+    AASIST_CUDA(cudaMemset(p.stats, 0, sizeof(long long) * 4 * grid));
+  }
   {
     LaunchSpan span(h, "sinc_frontend_tc", st);
     sinc_frontend_tc_kernel<<<grid, kFtThreads, smem, st>>>(p);
   }
   AASIST_CUDA(cudaGetLastError());
+  if (want_stats) {   // debugging aid: where the MMA warp waits (cycles per tile, mean over CTAs)
+    std::vector<long long> hst((size_t)4 * grid);
+    AASIST_CUDA(cudaStreamSynchronize(st));
+    AASIST_CUDA(cudaMemcpy(hst.data(), p.stats, sizeof(long long) * hst.size(), cudaMemcpyDeviceToHost));
+    double acc[3] = {0, 0, 0};
+    for (int c = 0; c < grid; ++c)
+      for (int k = 0; k < 3; ++k) acc[k] += (double)hst[(size_t)c * 4 + k] / grid;
+    const double tiles = (double)B * p.n_tiles_per_utt / grid;
+    fprintf(stderr, "[sinc_frontend_tc stats] per tile cycles: total %.0f | wait afull(producers) %.0f tempty(epilogue) %.0f | "
+            "issuing %.0f\n", acc[0] / tiles, acc[1] / tiles, acc[2] / tiles, (acc[0] - acc[1] - acc[2]) / tiles);
+    cudaFree(p.stats);
+  }
   return 0;
 }
 

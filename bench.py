@@ -29,8 +29,8 @@ FLOPS_PER_UTT = {"AASIST": 19.1241e9, "AASIST-L": 13.2063e9, "RawGAT-ST": 37.044
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--model", default="AASIST", choices=["AASIST", "AASIST-L", "RawGAT-ST"])
     ap.add_argument("--batch", type=int, default=512)
