@@ -31,7 +31,7 @@ constexpr int kB0Slab = 17 * 1024;          // one v tile (136 rows x 128 B, SWI
 constexpr int kB0A1Bytes = 17 * 256;        // im2col tile: 136 rows x 32 B, no-swizzle canonical
 constexpr int kB0A1Stride = 4608;
 constexpr int kB0DsBytes = 16 * 256;        // downsample im2col tile: 128 rows x 32 B
-constexpr int kB0NA1 = 4, kB0ND1 = 6, kB0NDS = 2;
+constexpr int kB0NA1 = 8, kB0ND1 = 6, kB0NDS = 3;
 constexpr int kB0Threads = 640;
 constexpr int kB0ZW = 400;                  // z columns kept per row: 3*j0-4 .. 3*j0+395 (392 used)
 constexpr int kB0W2Bytes = 6 * 32 * 128;    // conv2 weight image (6 taps x [32 rows x 128 B])
@@ -91,14 +91,14 @@ block0_tc_kernel(const Block0Params p) {
   uint64_t* empty = bars + 8;              // [8]  v tile consumed (tcgen05.commit)
   uint64_t* tfull = bars + 16;             // [2]  conv2 accumulators complete
   uint64_t* tempty = bars + 18;            // [2]  ... drained (8 epilogue warps)
-  uint64_t* a1full = bars + 20;            // [4]  (2 producer warps)
-  uint64_t* a1empty = bars + 24;           // [4]
-  uint64_t* d1full = bars + 28;            // [6]  conv1 accumulator complete
-  uint64_t* d1empty = bars + 34;           // [6]  ... drained (8 transformer warps)
-  uint64_t* dsfull = bars + 40;            // [2]
-  uint64_t* dsempty = bars + 42;           // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 44);
-  float* s_b1 = reinterpret_cast<float*>(bars + 46);     // [32] conv1 bias, broadcast reads by the transformers
+  uint64_t* a1full = bars + 20;            // [kB0NA1]  (3 producer warps)
+  uint64_t* a1empty = a1full + kB0NA1;     // [kB0NA1]
+  uint64_t* d1full = a1empty + kB0NA1;     // [kB0ND1]  conv1 accumulator complete
+  uint64_t* d1empty = d1full + kB0ND1;     // [kB0ND1]  ... drained (4 transformer warps)
+  uint64_t* dsfull = d1empty + kB0ND1;     // [kB0NDS]
+  uint64_t* dsempty = dsfull + kB0NDS;     // [kB0NDS]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(dsempty + kB0NDS);
+  float* s_b1 = reinterpret_cast<float*>(dsempty + kB0NDS + 2);   // [32] conv1 bias, broadcast reads by the transformers
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_strips = p.B * p.n_jt;
