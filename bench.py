@@ -330,9 +330,9 @@ def run_native(args):
         ach = (flops_step / n_launch) / (avg_launch_ms * 1e-3) / 1e12
         traffic = None
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-            if name == "AASIST" and B // n_launch == tr.get("utterances_per_launch"):
-                traffic = tr.get(top["kernel"])
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["bytes_per_utterance"]
+            if name == "AASIST" and top["kernel"] in tr:
+                traffic = int(tr[top["kernel"]] * (B / n_launch))       # ncu DRAM bytes per launch
         except Exception:
             pass
         roofline = {"bound": "tensor", "kernel": top["kernel"], "achieved": ach, "peak": peak_tf,
