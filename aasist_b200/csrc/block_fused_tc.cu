@@ -7,10 +7,18 @@
 // Unfused, this block moves 93 MB per utterance for 4.1 GFLOP and is HBM-bound (profiles/README.md);
 // fused it reads x once from HBM (21 MB; the second tap row and the identity hit L2) and writes 7 MB.
 // Structure = block0_tc.cu with conv1 fed by TMA instead of an im2col producer:
-//   warp 0 TMA producer (x tiles, 130-row boxes) | warp 1 MMA issuer: conv1 of v row r+1 (merged wider-N
-//   groups, accumulators D1[r&1]) one row ahead of conv2 of v row r (two passes, accumulators D2) |
-//   warps 2-9 epilogue | warps 10-17 transformers (D1 -> bias, SELU, zero-pad mask, fp16 pairs -> v ring).
-// Work item: (utterance, strip of 126 pooled columns).
+//   warp 0 TMA producer (x tiles, 130-row boxes, every tile loaded once) | warp 1 MMA issuer: conv1 one v row
+//   ahead of conv2 | warps 2-9 epilogue | warps 10-17 transformers (D1 -> bias, SELU, zero-pad mask, fp16
+//   pairs -> v ring).  Work item: (utterance, strip of 126 pooled columns).
+//
+// The MMAs are bound by their ~53-cycle issue/operand-fetch floor, not by math, so every A tile is used by as FEW
+// instructions as possible: an input row feeds the output row it completes (tap row dh=1) and the one it
+// starts (dh=0), and the two accumulator rows sit side by side in TMEM -- columns [phase s][slot][32 ch] --
+// so ONE wider-N MMA (N = 64 / 128 / 192 for 1 / 2 / 3 merged column taps) serves both.  The B rows follow
+// the same order; because a row changes role (new -> old) between consecutive steps while it stays in
+// its slot, shared memory holds the weight image in both slot orders.  A merged MMA has one accumulate flag
+// for all its columns, so accumulators are never overwritten: whoever drains a slot (epilogue / transformer
+// warps) stores zeros back with tcgen05.st before releasing it, and every MMA accumulates.
 #include <stdio.h>
 
 #include <algorithm>
@@ -26,9 +34,10 @@ using namespace ptx;
 constexpr int kBfStrip = 126;
 constexpr int kBfSlab = 17 * 1024;
 constexpr int kBfRows = 130;                // TMA box rows (j0-2 .. j0+127)
-constexpr int kBfThreads = 576;
+constexpr int kBfTGroups = 2;                // transformer groups of four warps (tiles dealt round-robin)
+constexpr int kBfThreads = 32 * (10 + 4 * kBfTGroups);   // 18 warps: 96 registers per thread
 constexpr int kBfWBytes = 6 * 32 * 128;     // one 32->32 weight image (taps stored dw = 2,1,0 per dh)
-constexpr int kBfNX = 4;                    // x ring slots (TMA)
+constexpr int kBfMaxX = 4;                  // x ring slots (TMA), upper bound
 
 struct BlockFusedParams {
   const __half* x;         // block input pairs [B][23][3][J][64] (identity operand)
@@ -38,7 +47,7 @@ struct BlockFusedParams {
   const uint8_t* w2img;    // conv2 image
   const float* b1;         // [32]
   const float* b2;         // [32]
-  int B, W, J, Wo, Jn, n_jt, n_vslots, Co;
+  int B, W, J, Wo, Jn, n_jt, n_vslots, n_xslots, Co;
   long long* stats;        // optional: MMA-warp wait cycles per CTA [total, d1empty, xfull, vfull, tempty]
 };
 
@@ -71,11 +80,11 @@ __global__ void __launch_bounds__(kBfThreads, 1)
 block_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const BlockFusedParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* s_w1 = smem;
-  uint8_t* s_w2 = smem + kBfWBytes;
-  uint8_t* s_v = smem + 2 * kBfWBytes;                         // v ring
+  uint8_t* s_w1 = smem;                                        // conv1 image, slot order 0 then 1
+  uint8_t* s_w2 = smem + 2 * kBfWBytes;                        // conv2 image, slot order 0 then 1
+  uint8_t* s_v = smem + 4 * kBfWBytes;                         // v ring
   uint8_t* s_x = s_v + (size_t)p.n_vslots * kBfSlab;           // x ring
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_x + kBfNX * kBfSlab);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_x + (size_t)p.n_xslots * kBfSlab);
   uint64_t* vfull = bars;                  // [8]  v tile written (4 transformer warps)
   uint64_t* vempty = bars + 8;             // [8]
   uint64_t* tfull = bars + 16;             // [2]  conv2 accumulators complete
@@ -86,22 +95,30 @@ block_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const BlockFusedP
   uint64_t* d1empty = bars + 30;           // [2]  drained (3 phase tiles x 4 warps)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 32);
   float* s_b1 = reinterpret_cast<float*>(bars + 34);
+  float* s_b2 = s_b1 + 32;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_strips = p.B * p.n_jt;
 
-  for (int i = threadIdx.x; i < kBfWBytes / 16; i += kBfThreads) {
-    reinterpret_cast<uint4*>(s_w1)[i] = __ldg(reinterpret_cast<const uint4*>(p.w1img) + i);
-    reinterpret_cast<uint4*>(s_w2)[i] = __ldg(reinterpret_cast<const uint4*>(p.w2img) + i);
+  // weight images: global [dh][tap 2,1,0][32 rows] -> shared [conv][order o][tap][slot][32 rows], where
+  // slot sigma of order o holds tap row dh = sigma ^ o (4 KB blocks, swizzle pattern preserved)
+  for (int i = threadIdx.x; i < 4 * kBfWBytes / 16; i += kBfThreads) {
+    const int blk = i >> 8, within = i & 255;
+    const int conv = blk / 12, o = (blk / 6) & 1, tap = (blk % 6) >> 1, sigma = blk & 1;
+    const uint8_t* src = (conv ? p.w2img : p.w1img) + (size_t)(((sigma ^ o) * 3 + tap) * 4096);
+    reinterpret_cast<uint4*>(smem)[i] = __ldg(reinterpret_cast<const uint4*>(src) + within);
   }
   for (int i = threadIdx.x; i < p.n_vslots * kBfSlab / 16; i += kBfThreads)
     reinterpret_cast<uint4*>(s_v)[i] = make_uint4(0, 0, 0, 0);   // rows 128..135 are read by discarded rows only
-  if (threadIdx.x < 32) s_b1[threadIdx.x] = __ldg(p.b1 + threadIdx.x);
+  if (threadIdx.x < 32) {
+    s_b1[threadIdx.x] = __ldg(p.b1 + threadIdx.x);
+    s_b2[threadIdx.x] = __ldg(p.b2 + threadIdx.x);
+  }
   fence_proxy_async_smem();
   if (threadIdx.x == 0) {
     for (int i = 0; i < 8; ++i) { mbar_init(&vfull[i], 4); mbar_init(&vempty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
-    for (int i = 0; i < kBfNX; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 1); }
+    for (int i = 0; i < kBfMaxX; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&d1full[i], 1); mbar_init(&d1empty[i], 12); }
     fence_barrier_init();
     prefetch_tensormap(&tmX);
@@ -111,7 +128,17 @@ block_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const BlockFusedP
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
-  constexpr int D1_COL0 = 192;             // TMEM: [0,192) conv2 accumulators, [192,384) conv1 accumulators
+  // TMEM: [0,192) conv2 accumulators, [192,384) conv1 accumulators; column = s*64 + slot*32 + channel
+  constexpr int D1_COL0 = 192;
+  if (warp >= 2) {                         // accumulators start at zero (and return to zero after every drain)
+    const uint32_t tz = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(((warp - 2) >> 2) * 96);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) tmem_st16_zero(tz + (uint32_t)(c * 16));
+    tmem_st_wait();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
 
   if (warp == 0) {
     // ======================================= TMA producer ======================================
@@ -121,16 +148,12 @@ block_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const BlockFusedP
       for (int t = blockIdx.x; t < n_strips; t += gridDim.x) {
         const int jt = t % p.n_jt, b = t / p.n_jt;
         const int jbox = jt * kBfStrip - 2;                      // x tile row a <-> j = j0 - 2 + a
-        for (int r = 0; r < 24; ++r)                             // v row r <- x rows r-1 (dh=0), r (dh=1)
-          for (int dh = 0; dh < 2; ++dh) {
-            const int xr = r + dh - 1;
-            if (xr < 0 || xr > 22) continue;                     // conv1 zero padding: no tile, no MMA
-            for (int phi = 0; phi < 3; ++phi) {
-              mbar_wait(&xempty[slot], phase ^ 1);
-              mbar_arrive_expect_tx(&xfull[slot], kBfRows * 128);
-              tma_load_5d(s_x + (size_t)slot * kBfSlab, &tmX, &xfull[slot], 0, jbox, phi, xr, b);
-              if (++slot == kBfNX) { slot = 0; phase ^= 1; }
-            }
+        for (int xr = 0; xr < 23; ++xr)                          // x row xr: completes v row xr, starts v row xr+1
+          for (int phi = 0; phi < 3; ++phi) {
+            mbar_wait(&xempty[slot], phase ^ 1);
+            mbar_arrive_expect_tx(&xfull[slot], kBfRows * 128);
+            tma_load_5d(s_x + (size_t)slot * kBfSlab, &tmX, &xfull[slot], 0, jbox, phi, xr, b);
+            if (++slot == p.n_xslots) { slot = 0; phase ^= 1; }
           }
       }
     }
@@ -141,114 +164,97 @@ block_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const BlockFusedP
     const uint32_t v_base = smem_u32(s_v), x_base = smem_u32(s_x);
     int xslot = 0, vslot = 0;
     uint32_t xphase = 0, vphase = 0;
-    int nrow1 = 0;                         // v rows whose conv1 has been issued (D1 buffer = nrow1 & 1)
-    int nstart = 0;                        // conv2 output rows started
+    int vbase = 0;                         // global index of this strip's v row 0 (v row n lives in D1 slot n & 1)
+    int g2 = 0;                            // conv2 steps issued (step g starts an output row in D2 slot g & 1)
     long long w_d1 = 0, w_x = 0, w_v = 0, w_t = 0;
     const long long t_begin = clock64();
 
-    // merged wider-N groups of one input tile (see conv_tc_kernel::issue_group)
-    auto mma3 = [&](uint32_t d_tmem, uint32_t a_row, uint32_t w_row, int ntaps, bool fresh) {
-      const uint32_t idesc = ntaps == 3 ? umma_idesc_f16(128, 96)
-                                        : (ntaps == 2 ? umma_idesc_f16(128, 64) : umma_idesc_f16(128, 32));
+    // one A tile (128 rows x [hi|lo]) against `ntaps` merged column taps x both slots: N = 64 * ntaps,
+    // three fp16 products, everything accumulates (the slots were zeroed when they were drained)
+    auto mma3 = [&](uint32_t d_tmem, uint32_t a_row, uint32_t w_row, int ntaps) {
+      const uint32_t idesc = ntaps == 3 ? umma_idesc_f16(128, 192)
+                                        : (ntaps == 2 ? umma_idesc_f16(128, 128) : umma_idesc_f16(128, 64));
       const uint64_t a_hi = umma_desc_sw128(a_row), a_lo = umma_desc_sw128(a_row + 64);
       const uint64_t w_hi = umma_desc_sw128(w_row), w_lo = umma_desc_sw128(w_row + 64);
 #pragma unroll
       for (int kc = 0; kc < 2; ++kc) {
-        umma_f16(d_tmem, a_hi + 2 * kc, w_hi + 2 * kc, idesc, (kc > 0 || !fresh) ? 1u : 0u);
+        umma_f16(d_tmem, a_hi + 2 * kc, w_hi + 2 * kc, idesc, 1);
         umma_f16(d_tmem, a_lo + 2 * kc, w_hi + 2 * kc, idesc, 1);
         umma_f16(d_tmem, a_hi + 2 * kc, w_lo + 2 * kc, idesc, 1);
       }
     };
-    auto issue_group = [&](uint32_t a_slot, uint32_t wb, int phi, uint32_t d0, bool fresh) {
+    // pool phase s is served by column tap dw with (s + dw - 1) == phi (mod 3), from A rows shifted by
+    // floor((s + dw - 1) / 3); taps are stored dw = 2,1,0 (8 KB each: both slots), D columns s*64
+    auto issue_group = [&](uint32_t a_slot, uint32_t wb, int phi, uint32_t d0) {
       if (phi == 1) {
-        mma3(d0, a_slot + 128, wb, 3, fresh);
+        mma3(d0, a_slot + 128, wb, 3);
       } else if (phi == 0) {
-        mma3(d0, a_slot + 128, wb + 4096, 2, fresh);
-        mma3(d0 + 64, a_slot + 256, wb, 1, fresh);
+        mma3(d0, a_slot + 128, wb + 8192, 2);
+        mma3(d0 + 128, a_slot + 256, wb, 1);
       } else {
-        mma3(d0 + 32, a_slot + 128, wb, 2, fresh);
-        mma3(d0, a_slot, wb + 8192, 1, fresh);
+        mma3(d0 + 64, a_slot + 128, wb, 2);
+        mma3(d0, a_slot, wb + 16384, 1);
       }
     };
-    auto conv1_row = [&](int r) {          // all x tiles of v row r into D1[nrow1 & 1]
-      const int buf = nrow1 & 1;
-      { long long c0 = clock64(); mbar_wait(&d1empty[buf], ((nrow1 >> 1) & 1) ^ 1); w_d1 += clock64() - c0; }
+    auto d1_claim = [&](int n) {           // v row n is about to receive its first MMA: its slot must be drained
+      long long c0 = clock64();
+      mbar_wait(&d1empty[n & 1], ((n >> 1) & 1) ^ 1);
+      w_d1 += clock64() - c0;
+    };
+    auto conv1_step = [&](int h) {         // x row h: dh=1 completes v row h, dh=0 starts v row h+1
+      const int n_old = vbase + h, n_new = n_old + 1;
+      if (h == 0) d1_claim(n_old);         // v row 0 has no dh=0 contribution (zero padding): it starts here
+      d1_claim(n_new);
       tc_fence_after_sync();
-      const uint32_t d0 = tmem_base + (uint32_t)(D1_COL0 + buf * 96);
-      bool fresh = true;
-      for (int dh = 0; dh < 2; ++dh) {
-        const int xr = r + dh - 1;
-        if (xr < 0 || xr > 22) continue;
-        for (int phi = 0; phi < 3; ++phi) {
-          { long long c0 = clock64(); mbar_wait(&xfull[xslot], xphase); w_x += clock64() - c0; }
-          tc_fence_after_sync();
-          if (leader) {
-            issue_group(x_base + (uint32_t)xslot * kBfSlab, w1_base + (uint32_t)(dh * 3 * 4096), phi, d0,
-                        fresh && phi == 0);
-            umma_commit(&xempty[xslot]);
-          }
-          __syncwarp();
-          if (++xslot == kBfNX) { xslot = 0; xphase ^= 1; }
+      const uint32_t wb = w1_base + (uint32_t)((n_new & 1) * kBfWBytes);   // order o: slot (n_new & 1) gets dh=0
+      for (int phi = 0; phi < 3; ++phi) {
+        { long long c0 = clock64(); mbar_wait(&xfull[xslot], xphase); w_x += clock64() - c0; }
+        tc_fence_after_sync();
+        if (leader) {
+          issue_group(x_base + (uint32_t)xslot * kBfSlab, wb, phi, tmem_base + (uint32_t)D1_COL0);
+          umma_commit(&xempty[xslot]);
         }
-        fresh = false;
+        __syncwarp();
+        if (++xslot == p.n_xslots) { xslot = 0; xphase ^= 1; }
       }
-      if (leader) umma_commit(&d1full[buf]);
+      if (leader) {
+        umma_commit(&d1full[n_old & 1]);
+        if (h == 22) umma_commit(&d1full[n_new & 1]);                // v row 23 has no dh=1 contribution
+      }
       __syncwarp();
-      ++nrow1;
     };
-    auto vadvance = [&](int& sl, uint32_t& ph) {
-      if (++sl == p.n_vslots) { sl = 0; ph ^= 1; }
+    auto conv2_step = [&]() {              // v row r: dh=1 completes output row r-1, dh=0 starts output row r
+      const int g = g2++;
+      // slot g & 1 was last completed by step g-1 (the epilogue's (g-1)>>1-th drain of that slot); g = 0: none
+      { long long c0 = clock64(); mbar_wait(&tempty[g & 1], (uint32_t)(((g - 1) >> 1) & 1)); w_t += clock64() - c0; }
+      tc_fence_after_sync();
+      const uint32_t wb = w2_base + (uint32_t)((g & 1) * kBfWBytes);
+      for (int phi = 0; phi < 3; ++phi) {
+        { long long c0 = clock64(); mbar_wait(&vfull[vslot], vphase); w_v += clock64() - c0; }
+        tc_fence_after_sync();
+        if (leader) {
+          issue_group(v_base + (uint32_t)vslot * kBfSlab, wb, phi, tmem_base);
+          umma_commit(&vempty[vslot]);
+        }
+        __syncwarp();
+        if (++vslot == p.n_vslots) { vslot = 0; vphase ^= 1; }
+      }
+      // the row in the other slot is complete.  For v row 0 that "row" is a dummy (output row -1: it holds the
+      // dh=0 product of the previous strip's v row 23 plus this dh=1 product); the epilogue just clears it.
+      if (leader) umma_commit(&tfull[(g & 1) ^ 1]);
+      __syncwarp();
     };
 
     for (int t = blockIdx.x; t < n_strips; t += gridDim.x) {
-      int buf_open = 0;
-      conv1_row(0);
+      conv1_step(0);
       for (int r = 0; r < 24; ++r) {
-        if (r < 23) conv1_row(r + 1);                            // one v row ahead of conv2
-        const bool has_o1 = r >= 1, has_o0 = r <= 22;
-        int sl[3];
-        uint32_t ph[3];
-        {
-          int s2 = vslot;
-          uint32_t p2 = vphase;
-          for (int i = 0; i < 3; ++i) { sl[i] = s2; ph[i] = p2; vadvance(s2, p2); }
-        }
-        for (int phi = 0; phi < 3; ++phi) {                      // pass 1: dh=1 completes output row r-1
-          { long long c0 = clock64(); mbar_wait(&vfull[sl[phi]], ph[phi]); w_v += clock64() - c0; }
-          tc_fence_after_sync();
-          if (has_o1 && leader)
-            issue_group(v_base + (uint32_t)sl[phi] * kBfSlab, w2_base + 3 * 4096, phi,
-                        tmem_base + (uint32_t)(buf_open * 96), false);
-          __syncwarp();
-        }
-        if (has_o1) {
-          if (leader) umma_commit(&tfull[buf_open]);
-          __syncwarp();
-        }
-        if (has_o0) {                                            // pass 2: dh=0 starts output row r
-          buf_open = nstart & 1;
-          { long long c0 = clock64(); mbar_wait(&tempty[buf_open], ((nstart >> 1) & 1) ^ 1); w_t += clock64() - c0; }
-          tc_fence_after_sync();
-          ++nstart;
-          for (int phi = 0; phi < 3; ++phi) {
-            if (leader) {
-              issue_group(v_base + (uint32_t)sl[phi] * kBfSlab, w2_base, phi, tmem_base + (uint32_t)(buf_open * 96),
-                          phi == 0);
-              umma_commit(&vempty[sl[phi]]);
-            }
-            __syncwarp();
-          }
-        } else {
-          for (int phi = 0; phi < 3; ++phi) {
-            if (leader) umma_commit(&vempty[sl[phi]]);
-            __syncwarp();
-          }
-        }
-        for (int i = 0; i < 3; ++i) vadvance(vslot, vphase);
+        if (r + 1 <= 22) conv1_step(r + 1);                        // one v row ahead of conv2
+        conv2_step();
       }
+      vbase += 24;
     }
     if (p.stats && leader) {
-      long long* stt = p.stats + (size_t)blockIdx.x * 8;
+      long long* stt = p.stats + (size_t)blockIdx.x * 16;
       stt[0] = clock64() - t_begin; stt[1] = w_d1; stt[2] = w_x; stt[3] = w_v; stt[4] = w_t;
     }
   } else if (warp >= 2 && warp < 10) {
@@ -256,74 +262,95 @@ block_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const BlockFusedP
     const int quad = warp & 3, half = (warp - 2) >> 2;
     const int m = quad * 32 + lane;
     const int col0 = half * 16;
-    float bias[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) bias[i] = __ldg(p.b2 + col0 + i);
-    int tcount = 0;
+    int tcount = 0;                        // completed conv2 steps (24 per strip; the first is the dummy row -1)
     for (int t = blockIdx.x; t < n_strips; t += gridDim.x) {
       const int jt = t % p.n_jt, b = t / p.n_jt;
       const int j = jt * kBfStrip + m;
       const bool live = m < kBfStrip;
       const bool valid = j < p.Wo;
-      for (int h = 0; h < 23; ++h, ++tcount) {
-        const int buf = tcount & 1;
-        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 96 + col0);
+      const int jc = min(j, p.J - 1);                              // j >= J is never stored: any address will do
+      // The identity operand x[b][h][s][j][col0..col0+16) (hi + lo) of the NEXT row is fetched from L2 while this
+      // thread would otherwise idle, summed to fp32 and parked in spare TMEM columns [384,480): it costs no
+      // registers across the wait for the accumulators, and its latency is off the drain path.
+      const uint32_t t_idn = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(384 + col0);
+      for (int h = -1; h < 23; ++h, ++tcount) {
+        const int buf = (tcount & 1) ^ 1;
+        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 32 + col0);
         mbar_wait(&tfull[buf], (tcount >> 1) & 1);
         tc_fence_after_sync();
         uint32_t acc[3][16];
+        if (h >= 0) {
 #pragma unroll
-        for (int s = 0; s < 3; ++s) tmem_ld16_async(t_row + (uint32_t)(s * 32), acc[s]);
+          for (int s = 0; s < 3; ++s) tmem_ld16_async(t_row + (uint32_t)(s * 64), acc[s]);
 #pragma unroll
-        for (int s = 0; s < 3; ++s) tmem_ld_wait16(acc[s]);
+          for (int s = 0; s < 3; ++s) tmem_ld_wait16(acc[s]);
+        }
+#pragma unroll
+        for (int s = 0; s < 3; ++s) tmem_st16_zero(t_row + (uint32_t)(s * 64));
+        tmem_st_wait();
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[buf]);
-        if (!live) continue;
         float mx[16];
+        if (h >= 0) {
 #pragma unroll
-        for (int s = 0; s < 3; ++s) {
-          // identity operand x[b][h][s][j][col0..col0+16) (L2-resident: conv1 just read this row)
-          uint32_t ih[8], il[8];
-          if (j < p.J) {
-            const __half* xs = p.x + ((((size_t)b * 23 + h) * 3 + s) * p.J + j) * 64 + col0;
-            ld_global_nc_256(xs, ih);
-            ld_global_nc_256(xs + 32, il);                       // lo half-row: 32 halves = 64 B later
-          } else {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) ih[k] = il[k] = 0u;
-          }
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const float2 fa = __half22float2(*reinterpret_cast<const __half2*>(&ih[k]));
-            const float2 fb = __half22float2(*reinterpret_cast<const __half2*>(&il[k]));
-            const float v0 = __uint_as_float(acc[s][2 * k]) + (fa.x + fb.x);
-            const float v1 = __uint_as_float(acc[s][2 * k + 1]) + (fa.y + fb.y);
-            mx[2 * k] = s == 0 ? v0 : fmaxf(mx[2 * k], v0);
-            mx[2 * k + 1] = s == 0 ? v1 : fmaxf(mx[2 * k + 1], v1);
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) mx[i] = valid ? mx[i] + bias[i] : 0.f;
-        if (p.out_f32) {
-          if (valid)
+          for (int s = 0; s < 3; ++s) {
+            uint32_t idn[16];
+            tmem_ld16_async(t_idn + (uint32_t)(s * 32), idn);
+            tmem_ld_wait16(idn);
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const int ch = col0 + i;
-              if (ch < p.Co) p.out_f32[(((size_t)b * p.Co + ch) * 23 + h) * p.Wo + j] = mx[i];
+              const float v = __uint_as_float(acc[s][i]) + __uint_as_float(idn[i]);
+              mx[i] = s == 0 ? v : fmaxf(mx[i], v);
             }
-        } else if (j / 3 < p.Jn) {
-          uint32_t hw[8], lw[8];
+          }
+        }
+        if (live && h >= 0) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) bf_split2<false>(mx[2 * i], mx[2 * i + 1], hw[i], lw[i]);
-          __half* o = p.out + ((((size_t)b * 23 + h) * 3 + (j % 3)) * p.Jn + j / 3) * 64 + col0;
-          st_global_256(o, hw);
-          st_global_256(o + 32, lw);
+          for (int i = 0; i < 16; ++i) mx[i] = valid ? mx[i] + s_b2[col0 + i] : 0.f;
+          if (p.out_f32) {
+            if (valid)
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int ch = col0 + i;
+                if (ch < p.Co) p.out_f32[(((size_t)b * p.Co + ch) * 23 + h) * p.Wo + j] = mx[i];
+              }
+          } else if (j / 3 < p.Jn) {
+            uint32_t hw[8], lw[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) bf_split2<false>(mx[2 * i], mx[2 * i + 1], hw[i], lw[i]);
+            __half* o = p.out + ((((size_t)b * 23 + h) * 3 + (j % 3)) * p.Jn + j / 3) * 64 + col0;
+            st_global_256(o, hw);
+            st_global_256(o + 32, lw);
+          }
+        }
+        if (h < 22) {                                              // park the next row's identity operand
+          const __half* xs = p.x + (((size_t)b * 23 + (h + 1)) * 3 * p.J + jc) * 64 + col0;
+          uint32_t ih[3][8], il[3][8];
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            ld_global_nc_256(xs + (size_t)s * p.J * 64, ih[s]);
+            ld_global_nc_256(xs + (size_t)s * p.J * 64 + 32, il[s]);   // lo half-row: 32 halves = 64 B later
+          }
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            uint32_t sum[16];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float2 fa = __half22float2(*reinterpret_cast<const __half2*>(&ih[s][k]));
+              const float2 fb = __half22float2(*reinterpret_cast<const __half2*>(&il[s][k]));
+              sum[2 * k] = __float_as_uint(fa.x + fb.x);
+              sum[2 * k + 1] = __float_as_uint(fa.y + fb.y);
+            }
+            tmem_st16(t_idn + (uint32_t)(s * 32), sum);
+          }
+          tmem_st_wait();
         }
       }
     }
   } else if (warp >= 10) {
     // ============ transformers: D1 (TMEM) -> bias, SELU, zero-pad mask, fp16 pairs -> swizzled v tile ============
-    const int quad = warp & 3, grp = (warp - 10) >> 2;           // two groups of four warps take alternate tiles
+    const int quad = warp & 3, grp = (warp - 10) >> 2;           // groups of four warps take tiles round-robin
     const int jj = quad * 32 + lane;
     const uint32_t row_off = (uint32_t)jj * 128;
     const uint32_t sw = (uint32_t)(jj & 7);
@@ -335,17 +362,20 @@ block_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const BlockFusedP
       for (int r = 0; r < 24; ++r, ++nrow) {
         const int buf = nrow & 1;
         for (int s = 0; s < 3; ++s, ++n) {
-          if ((n & 1) == grp) {
+          if (n % kBfTGroups == grp) {
             const int pos = 3 * j + s;
             const bool valid = j >= 0 && pos < p.W;              // conv2 zero-pads v itself
             mbar_wait(&d1full[buf], (nrow >> 1) & 1);
             tc_fence_after_sync();
             uint32_t acc[2][16];
-            const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(D1_COL0 + buf * 96 + s * 32);
+            const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(D1_COL0 + s * 64 + buf * 32);
             tmem_ld16_async(ta, acc[0]);
             tmem_ld16_async(ta + 16, acc[1]);
             tmem_ld_wait16(acc[0]);
             tmem_ld_wait16(acc[1]);
+            tmem_st16_zero(ta);
+            tmem_st16_zero(ta + 16);
+            tmem_st_wait();
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&d1empty[buf]);
@@ -393,9 +423,12 @@ int launch_block_fused_tc(aasist_handle* h, int sm_count, const char* name, cons
   p.x = x; p.out = out; p.out_f32 = out_f32; p.w1img = w1img; p.w2img = w2img; p.b1 = b1; p.b2 = b2;
   p.B = nb; p.W = W; p.J = (W + 2) / 3; p.Wo = W / 3; p.Jn = (p.Wo + 2) / 3; p.Co = Co;
   p.n_jt = (std::max(p.J, 3 * p.Jn) + kBfStrip - 1) / kBfStrip;
-  const int fixed = 1024 + 2 * kBfWBytes + kBfNX * kBfSlab + 512;
+  static int xslots = -1;
+  if (xslots < 0) { const char* e = getenv("AASIST_BF_XSLOTS"); xslots = e ? std::min(kBfMaxX, std::max(2, atoi(e))) : 3; }
+  p.n_xslots = xslots;
+  const int fixed = 1024 + 4 * kBfWBytes + p.n_xslots * kBfSlab + 1024;
   p.n_vslots = std::min(8, (227 * 1024 - fixed) / kBfSlab);
-  if (p.n_vslots < 6) {
+  if (p.n_vslots < 3) {
     set_error("block_fused_tc: shared memory budget allows only %d v-ring slots", p.n_vslots);
     return AASIST_E_INVALID;
   }
@@ -406,8 +439,8 @@ int launch_block_fused_tc(aasist_handle* h, int sm_count, const char* name, cons
   if (want_stats < 0) { const char* e = getenv("AASIST_BF_STATS"); want_stats = e ? atoi(e) : 0; }
   p.stats = nullptr;
   if (want_stats) {
-    AASIST_CUDA(cudaMalloc(&p.stats, sizeof(long long) * 8 * grid));
-    AASIST_CUDA(cudaMemset(p.stats, 0, sizeof(long long) * 8 * grid));
+    AASIST_CUDA(cudaMalloc(&p.stats, sizeof(long long) * 16 * grid));
+    AASIST_CUDA(cudaMemset(p.stats, 0, sizeof(long long) * 16 * grid));
   }
   {
     LaunchSpan span(h, name, st);
@@ -415,12 +448,12 @@ int launch_block_fused_tc(aasist_handle* h, int sm_count, const char* name, cons
   }
   AASIST_CUDA(cudaGetLastError());
   if (want_stats) {   // debugging aid: where the MMA warp waits (cycles per row-tile, mean over CTAs)
-    std::vector<long long> hst((size_t)8 * grid);
+    std::vector<long long> hst((size_t)16 * grid);
     AASIST_CUDA(cudaStreamSynchronize(st));
     AASIST_CUDA(cudaMemcpy(hst.data(), p.stats, sizeof(long long) * hst.size(), cudaMemcpyDeviceToHost));
-    double acc[5] = {0, 0, 0, 0, 0};
+    double acc[16] = {0};
     for (int c = 0; c < grid; ++c)
-      for (int k = 0; k < 5; ++k) acc[k] += (double)hst[(size_t)c * 8 + k] / grid;
+      for (int k = 0; k < 16; ++k) acc[k] += (double)hst[(size_t)c * 16 + k] / grid;
     const double rows = (double)nb * p.n_jt * 23 / grid;
     fprintf(stderr, "[%s stats] per row-tile cycles: total %.0f | wait d1empty %.0f xfull %.0f vfull %.0f tempty %.0f | "
             "issuing %.0f\n", name, acc[0] / rows, acc[1] / rows, acc[2] / rows, acc[3] / rows, acc[4] / rows,
