@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libaasist_b200.so")
+# AASIST_B200_LIB: developer override (kernel experiments build variant libraries next to the tree)
+LIB_PATH = os.environ.get("AASIST_B200_LIB") or os.path.join(_HERE, "csrc", "libaasist_b200.so")
 
 KIND_AASIST, KIND_RAWGAT_ST = 0, 1
 PREC_FP32, PREC_F16X3 = 0, 1

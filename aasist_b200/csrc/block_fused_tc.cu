@@ -34,8 +34,7 @@ using namespace ptx;
 constexpr int kBfStrip = 126;
 constexpr int kBfSlab = 17 * 1024;
 constexpr int kBfRows = 130;                // TMA box rows (j0-2 .. j0+127)
-constexpr int kBfTGroups = 2;                // transformer groups of four warps (tiles dealt round-robin)
-constexpr int kBfThreads = 32 * (10 + 4 * kBfTGroups);   // 18 warps: 96 registers per thread
+constexpr int kBfThreads = 576;              // 18 warps: 96 registers per thread
 constexpr int kBfWBytes = 6 * 32 * 128;     // one 32->32 weight image (taps stored dw = 2,1,0 per dh)
 constexpr int kBfMaxX = 4;                  // x ring slots (TMA), upper bound
 
@@ -85,14 +84,14 @@ block_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const BlockFusedP
   uint8_t* s_v = smem + 4 * kBfWBytes;                         // v ring
   uint8_t* s_x = s_v + (size_t)p.n_vslots * kBfSlab;           // x ring
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_x + (size_t)p.n_xslots * kBfSlab);
-  uint64_t* vfull = bars;                  // [8]  v tile written (4 transformer warps)
+  uint64_t* vfull = bars;                  // [8]  v tile written (8 transformer warps)
   uint64_t* vempty = bars + 8;             // [8]
   uint64_t* tfull = bars + 16;             // [2]  conv2 accumulators complete
   uint64_t* tempty = bars + 18;            // [2]  (8 epilogue warps)
   uint64_t* xfull = bars + 20;             // [4]  TMA
   uint64_t* xempty = bars + 24;            // [4]
   uint64_t* d1full = bars + 28;            // [2]  conv1 accumulators of a v row complete
-  uint64_t* d1empty = bars + 30;           // [2]  drained (3 phase tiles x 4 warps)
+  uint64_t* d1empty = bars + 30;           // [2]  drained (8 transformer warps)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 32);
   float* s_b1 = reinterpret_cast<float*>(bars + 34);
   float* s_b2 = s_b1 + 32;
@@ -116,10 +115,10 @@ block_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const BlockFusedP
   }
   fence_proxy_async_smem();
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 8; ++i) { mbar_init(&vfull[i], 4); mbar_init(&vempty[i], 1); }
+    for (int i = 0; i < 8; ++i) { mbar_init(&vfull[i], 8); mbar_init(&vempty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
     for (int i = 0; i < kBfMaxX; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&d1full[i], 1); mbar_init(&d1empty[i], 12); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&d1full[i], 1); mbar_init(&d1empty[i], 8); }
     fence_barrier_init();
     prefetch_tensormap(&tmX);
   }
@@ -329,8 +328,9 @@ block_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const BlockFusedP
           uint32_t ih[3][8], il[3][8];
 #pragma unroll
           for (int s = 0; s < 3; ++s) {
-            ld_global_nc_256(xs + (size_t)s * p.J * 64, ih[s]);
-            ld_global_nc_256(xs + (size_t)s * p.J * 64 + 32, il[s]);   // lo half-row: 32 halves = 64 B later
+            // (no L1 allocation: the L1 data array is the shared-memory array the MMAs fetch operands from)
+            ld_global_na_256(xs + (size_t)s * p.J * 64, ih[s]);
+            ld_global_na_256(xs + (size_t)s * p.J * 64 + 32, il[s]);   // lo half-row: 32 halves = 64 B later
           }
 #pragma unroll
           for (int s = 0; s < 3; ++s) {
@@ -349,60 +349,57 @@ block_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const BlockFusedP
       }
     }
   } else if (warp >= 10) {
-    // ============ transformers: D1 (TMEM) -> bias, SELU, zero-pad mask, fp16 pairs -> swizzled v tile ============
-    const int quad = warp & 3, grp = (warp - 10) >> 2;           // groups of four warps take tiles round-robin
+    // ============ transformers: D1 (TMEM) -> bias, SELU, zero-pad mask, fp16 pairs -> swizzled v tiles ============
+    // warp = (TMEM lane quadrant, 16-channel half); the whole v row (3 phase tiles) is read and its slot
+    // cleared and released at once, so conv1 can start the row after next while the math is still running
+    const int quad = warp & 3, half = (warp - 10) >> 2;
     const int jj = quad * 32 + lane;
+    const int col0 = half * 16;
     const uint32_t row_off = (uint32_t)jj * 128;
     const uint32_t sw = (uint32_t)(jj & 7);
-    int n = 0, slot = 0, nrow = 0;
+    const uint32_t c_hi = (uint32_t)(2 * half), c_lo = (uint32_t)(4 + 2 * half);   // 16-byte chunks of this half
+    int slot = 0, nrow = 0;
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < n_strips; t += gridDim.x) {
       const int jt = t % p.n_jt;
       const int j = jt * kBfStrip - 1 + jj;
       for (int r = 0; r < 24; ++r, ++nrow) {
         const int buf = nrow & 1;
-        for (int s = 0; s < 3; ++s, ++n) {
-          if (n % kBfTGroups == grp) {
-            const int pos = 3 * j + s;
-            const bool valid = j >= 0 && pos < p.W;              // conv2 zero-pads v itself
-            mbar_wait(&d1full[buf], (nrow >> 1) & 1);
-            tc_fence_after_sync();
-            uint32_t acc[2][16];
-            const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(D1_COL0 + s * 64 + buf * 32);
-            tmem_ld16_async(ta, acc[0]);
-            tmem_ld16_async(ta + 16, acc[1]);
-            tmem_ld_wait16(acc[0]);
-            tmem_ld_wait16(acc[1]);
-            tmem_st16_zero(ta);
-            tmem_st16_zero(ta + 16);
-            tmem_st_wait();
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&d1empty[buf]);
-            uint32_t hw[16], lw[16];
+        const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(D1_COL0 + buf * 32 + col0);
+        mbar_wait(&d1full[buf], (nrow >> 1) & 1);
+        tc_fence_after_sync();
+        uint32_t acc[3][16];
 #pragma unroll
-            for (int c = 0; c < 2; ++c)
+        for (int s = 0; s < 3; ++s) tmem_ld16_async(ta + (uint32_t)(s * 64), acc[s]);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float2 bb = *reinterpret_cast<const float2*>(s_b1 + c * 16 + 2 * i);
-                float x0 = bf_selu(__uint_as_float(acc[c][2 * i]) + bb.x);
-                float x1 = bf_selu(__uint_as_float(acc[c][2 * i + 1]) + bb.y);
-                if (!valid) { x0 = 0.f; x1 = 0.f; }
-                bf_split2<true>(x0, x1, hw[c * 8 + i], lw[c * 8 + i]);
-              }
-            mbar_wait(&vempty[slot], phase ^ 1);
-            uint8_t* row = s_v + (size_t)slot * kBfSlab + row_off;
+        for (int s = 0; s < 3; ++s) tmem_ld_wait16(acc[s]);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              *reinterpret_cast<uint4*>(row + (((uint32_t)q ^ sw) << 4)) =
-                  make_uint4(hw[4 * q], hw[4 * q + 1], hw[4 * q + 2], hw[4 * q + 3]);
-              *reinterpret_cast<uint4*>(row + (((uint32_t)(4 + q) ^ sw) << 4)) =
-                  make_uint4(lw[4 * q], lw[4 * q + 1], lw[4 * q + 2], lw[4 * q + 3]);
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&vfull[slot]);
+        for (int s = 0; s < 3; ++s) tmem_st16_zero(ta + (uint32_t)(s * 64));
+        tmem_st_wait();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&d1empty[buf]);
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const bool valid = j >= 0 && 3 * j + s < p.W;            // conv2 zero-pads v itself
+          uint32_t hw[8], lw[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float2 bb = *reinterpret_cast<const float2*>(s_b1 + col0 + 2 * i);
+            float x0 = bf_selu(__uint_as_float(acc[s][2 * i]) + bb.x);
+            float x1 = bf_selu(__uint_as_float(acc[s][2 * i + 1]) + bb.y);
+            if (!valid) { x0 = 0.f; x1 = 0.f; }
+            bf_split2<true>(x0, x1, hw[i], lw[i]);
           }
+          mbar_wait(&vempty[slot], phase ^ 1);
+          uint8_t* row = s_v + (size_t)slot * kBfSlab + row_off;
+          *reinterpret_cast<uint4*>(row + ((c_hi ^ sw) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint4*>(row + (((c_hi + 1) ^ sw) << 4)) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+          *reinterpret_cast<uint4*>(row + ((c_lo ^ sw) << 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          *reinterpret_cast<uint4*>(row + (((c_lo + 1) ^ sw) << 4)) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&vfull[slot]);
           if (++slot == p.n_vslots) { slot = 0; phase ^= 1; }
         }
       }

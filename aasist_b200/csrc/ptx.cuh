@@ -218,6 +218,12 @@ __device__ __forceinline__ void st_global_256(void* p, const uint32_t (&w)[8]) {
                "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
                : "memory");
 }
+// same, not allocating in L1: the L1 data array is the shared-memory array the MMAs read their operands from
+__device__ __forceinline__ void ld_global_na_256(const void* p, uint32_t (&w)[8]) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+               : "l"(p));
+}
 __device__ __forceinline__ void ld_global_nc_256(const void* p, uint32_t (&w)[8]) {
   asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
