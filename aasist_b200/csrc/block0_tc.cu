@@ -35,7 +35,10 @@ constexpr int kB0NA1 = 8, kB0ND1 = 6, kB0NDS = 3;
 constexpr int kB0Threads = 640;
 constexpr int kB0ZW = 400;                  // z columns kept per row: 3*j0-4 .. 3*j0+395 (392 used)
 constexpr int kB0W2Bytes = 6 * 32 * 128;    // conv2 weight image (6 taps x [32 rows x 128 B])
-constexpr int kB0ImgBytes = kB0W2Bytes + 2 * 1024 + 6 * 1024;   // + B1, B1' + 3 x (Bds, Bds')
+constexpr int kB0ImgBytes = kB0W2Bytes + 2 * 1024 + 6 * 1024;   // + B1, B1' + 3 x (Bds, Bds')   (global image)
+// shared-memory image: conv2 in both slot orders (see block_fused_tc.cu), B1, B1', and the downsample operands
+// spread over the [phase][slot] accumulator columns with zero blocks for the other slot: [0,B0,0,B1,0,B2,0] x 2
+constexpr int kB0SmemImgBytes = 2 * kB0W2Bytes + 2 * 1024 + 2 * 7 * 1024;
 
 struct Block0Params {
   const float* z;          // (B,23,W)
@@ -81,7 +84,7 @@ block0_tc_kernel(const Block0Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* s_w = smem;                                         // weight images
-  uint8_t* s_ring = smem + kB0ImgBytes;                        // v tiles
+  uint8_t* s_ring = smem + kB0SmemImgBytes;                    // v tiles
   uint8_t* s_a1 = s_ring + (size_t)p.n_slots * kB0Slab;        // conv1 im2col ring
   uint8_t* s_ds = s_a1 + kB0NA1 * kB0A1Stride;                 // downsample im2col ring
   __half* s_zh = reinterpret_cast<__half*>(s_ds + kB0NDS * kB0DsBytes);   // [3][kB0ZW] rolling rows of z, hi halves
@@ -99,16 +102,34 @@ block0_tc_kernel(const Block0Params p) {
   uint64_t* dsempty = dsfull + kB0NDS;     // [kB0NDS]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(dsempty + kB0NDS);
   float* s_b1 = reinterpret_cast<float*>(dsempty + kB0NDS + 2);   // [32] conv1 bias, broadcast reads by the transformers
+  float* s_b2 = s_b1 + 32;                                         // [32] conv2 + downsample bias
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_strips = p.B * p.n_jt;
 
-  for (int i = threadIdx.x; i < kB0ImgBytes / 16; i += kB0Threads)
-    reinterpret_cast<uint4*>(s_w)[i] = __ldg(reinterpret_cast<const uint4*>(p.wimg) + i);
+  // conv2: global [dh][tap 2,1,0][32 rows] -> shared [order o][tap][slot][32 rows], slot sigma of order o = dh sigma^o
+  for (int i = threadIdx.x; i < 2 * kB0W2Bytes / 16; i += kB0Threads) {
+    const int blk = i >> 8, within = i & 255;
+    const int o = blk / 6, tap = (blk % 6) >> 1, sigma = blk & 1;
+    reinterpret_cast<uint4*>(s_w)[i] =
+        __ldg(reinterpret_cast<const uint4*>(p.wimg + (size_t)(((sigma ^ o) * 3 + tap) * 4096)) + within);
+  }
+  for (int i = threadIdx.x; i < 2048 / 16; i += kB0Threads)     // B1, B1'
+    reinterpret_cast<uint4*>(s_w + 2 * kB0W2Bytes)[i] = __ldg(reinterpret_cast<const uint4*>(p.wimg + kB0W2Bytes) + i);
+  for (int i = threadIdx.x; i < 2 * 7 * 1024 / 16; i += kB0Threads) {   // downsample: [0,B0,0,B1,0,B2,0] hi, then lo
+    const int blk = i >> 6, within = i & 63;
+    const int part = blk / 7, k = blk % 7;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (k & 1) v = __ldg(reinterpret_cast<const uint4*>(p.wimg + kB0W2Bytes + 2048 + (size_t)((part * 3 + (k >> 1)) * 1024)) + within);
+    reinterpret_cast<uint4*>(s_w + 2 * kB0W2Bytes + 2048)[i] = v;
+  }
   // rows 128..135 of a v tile are read (by discarded accumulator rows) but never written: keep them finite
   for (int i = threadIdx.x; i < p.n_slots * kB0Slab / 16; i += kB0Threads)
     reinterpret_cast<uint4*>(s_ring)[i] = make_uint4(0, 0, 0, 0);
-  if (threadIdx.x < 32) s_b1[threadIdx.x] = __ldg(p.b1 + threadIdx.x);
+  if (threadIdx.x < 32) {
+    s_b1[threadIdx.x] = __ldg(p.b1 + threadIdx.x);
+    s_b2[threadIdx.x] = __ldg(p.b2 + threadIdx.x);
+  }
   fence_proxy_async_smem();
   if (threadIdx.x == 0) {
     for (int i = 0; i < 8; ++i) { mbar_init(&full[i], 4); mbar_init(&empty[i], 1); }
@@ -123,19 +144,29 @@ block0_tc_kernel(const Block0Params p) {
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
-  constexpr int D1_COL0 = 192;             // TMEM: [0,192) conv2 accumulators (2 x 3 x 32), [192,384) D1 ring
+  // TMEM: [0,192) conv2 accumulators, column = s*64 + slot*32 + channel; [192,384) D1 ring (one 32-column tile each)
+  constexpr int D1_COL0 = 192;
+  if (warp >= 2 && warp < 10) {            // conv2 accumulators start at zero and return to zero after every drain
+    const uint32_t tz = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(((warp - 2) >> 2) * 96);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) tmem_st16_zero(tz + (uint32_t)(c * 16));
+    tmem_st_wait();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
 
   if (warp == 1) {
     // ======================================= MMA issuer =======================================
     const bool leader = elect_one();
     const uint32_t w_base = smem_u32(s_w), ring_base = smem_u32(s_ring);
     const uint32_t a1_base = smem_u32(s_a1), ds_base = smem_u32(s_ds);
-    const uint32_t b1_addr = w_base + kB0W2Bytes, b1p_addr = b1_addr + 1024, bds_addr = b1_addr + 2048;
+    const uint32_t b1_addr = w_base + 2 * kB0W2Bytes, b1p_addr = b1_addr + 1024, bds_addr = b1_addr + 2048;
     constexpr uint32_t IDESC = umma_idesc_f16(128, 32);
     int n1 = 0;                            // conv1 tiles issued
     int slot = 0;
     uint32_t phase = 0;
-    int nstart = 0, nds = 0;
+    int g2 = 0, nds = 0;                   // conv2 steps issued (step g starts an output row in slot g & 1)
     long long w_a1 = 0, w_d1 = 0, w_vf = 0, w_te = 0, w_ds = 0;
     const long long t_begin = clock64();
 
@@ -156,92 +187,71 @@ block0_tc_kernel(const Block0Params p) {
         __syncwarp();
       }
     };
-    // conv2 MMAs of one v tile: pool phases that read the same A rows share one wider-N MMA
-    // (weights stored with taps dw = 2,1,0 contiguous; see conv_tc_kernel::issue_group)
-    auto mma3 = [&](uint32_t d_tmem, uint32_t a_row, uint32_t w_row, int ntaps, bool fresh) {
-      const uint32_t idesc = ntaps == 3 ? umma_idesc_f16(128, 96) : (ntaps == 2 ? umma_idesc_f16(128, 64) : IDESC);
+    // conv2 MMAs of one v tile.  Pool phases that read the same A rows share one wider-N MMA, and so do the
+    // two output rows the tile feeds (tap row dh=1 completes one, dh=0 starts the next): N = 64 / 128 / 192,
+    // everything accumulates (slots are cleared by the epilogue when it drains them) -- block_fused_tc.cu
+    auto mma3 = [&](uint32_t d_tmem, uint32_t a_row, uint32_t w_row, int ntaps) {
+      const uint32_t idesc = ntaps == 3 ? umma_idesc_f16(128, 192)
+                                        : (ntaps == 2 ? umma_idesc_f16(128, 128) : umma_idesc_f16(128, 64));
       const uint64_t a_hi = umma_desc_sw128(a_row), a_lo = umma_desc_sw128(a_row + 64);
       const uint64_t w_hi = umma_desc_sw128(w_row), w_lo = umma_desc_sw128(w_row + 64);
 #pragma unroll
       for (int kc = 0; kc < 2; ++kc) {
-        umma_f16(d_tmem, a_hi + 2 * kc, w_hi + 2 * kc, idesc, (kc > 0 || !fresh) ? 1u : 0u);
+        umma_f16(d_tmem, a_hi + 2 * kc, w_hi + 2 * kc, idesc, 1);
         umma_f16(d_tmem, a_lo + 2 * kc, w_hi + 2 * kc, idesc, 1);
         umma_f16(d_tmem, a_hi + 2 * kc, w_lo + 2 * kc, idesc, 1);
       }
     };
-    auto issue_group = [&](int slot_i, int dh, int phi, int buf, bool fresh) {
-      const uint32_t a_slot = ring_base + (uint32_t)slot_i * kB0Slab;
-      const uint32_t wb = w_base + (uint32_t)(dh * 3 * 4096);
-      const uint32_t d0 = tmem_base + (uint32_t)(buf * 96);
+    auto issue_group = [&](uint32_t a_slot, uint32_t wb, int phi) {
+      const uint32_t d0 = tmem_base;
       if (phi == 1) {
-        mma3(d0, a_slot + 128, wb, 3, fresh);
+        mma3(d0, a_slot + 128, wb, 3);
       } else if (phi == 0) {
-        mma3(d0, a_slot + 128, wb + 4096, 2, fresh);
-        mma3(d0 + 64, a_slot + 256, wb, 1, fresh);
+        mma3(d0, a_slot + 128, wb + 8192, 2);
+        mma3(d0 + 128, a_slot + 256, wb, 1);
       } else {
-        mma3(d0 + 32, a_slot + 128, wb, 2, fresh);
-        mma3(d0, a_slot, wb + 8192, 1, fresh);
+        mma3(d0 + 64, a_slot + 128, wb, 2);
+        mma3(d0, a_slot, wb + 16384, 1);
       }
-    };
-    auto advance = [&](int& sl, uint32_t& ph) {
-      if (++sl == p.n_slots) { sl = 0; ph ^= 1; }
     };
 
     for (int t = blockIdx.x; t < n_strips; t += gridDim.x) {
-      int buf_open = 0;
       issue_conv1_row();                                         // v row 0
       for (int r = 0; r < 24; ++r) {
         if (r < 23) issue_conv1_row();                           // v row r+1 (one row ahead of conv2)
-        const bool has_o1 = r >= 1, has_o0 = r <= 22;
-        int sl[3];
-        uint32_t ph[3];
-        {
-          int s2 = slot;
-          uint32_t p2 = phase;
-          for (int i = 0; i < 3; ++i) { sl[i] = s2; ph[i] = p2; advance(s2, p2); }
-        }
-        for (int phi = 0; phi < 3; ++phi) {                      // pass 1: dh=1 completes output row r-1
-          { long long c0 = clock64(); mbar_wait(&full[sl[phi]], ph[phi]); w_vf += clock64() - c0; }
+        // v row r: dh=1 completes output row r-1 (a dummy for r = 0, see block_fused_tc.cu), dh=0 starts row r
+        const int g = g2++;
+        { long long c0 = clock64(); mbar_wait(&tempty[g & 1], (uint32_t)(((g - 1) >> 1) & 1)); w_te += clock64() - c0; }
+        tc_fence_after_sync();
+        const uint32_t wb = w_base + (uint32_t)((g & 1) * kB0W2Bytes);
+        for (int phi = 0; phi < 3; ++phi) {
+          { long long c0 = clock64(); mbar_wait(&full[slot], phase); w_vf += clock64() - c0; }
           tc_fence_after_sync();
-          if (has_o1 && leader) issue_group(sl[phi], 1, phi, buf_open, false);
-          __syncwarp();
-        }
-        if (has_o1) {
-          if (leader) umma_commit(&tfull[buf_open]);
-          __syncwarp();
-        }
-        if (has_o0) {                                            // pass 2: dh=0 starts output row r
-          buf_open = nstart & 1;
-          { long long c0 = clock64(); mbar_wait(&tempty[buf_open], ((nstart >> 1) & 1) ^ 1); w_te += clock64() - c0; }
-          tc_fence_after_sync();
-          ++nstart;
-          for (int phi = 0; phi < 3; ++phi) {
-            if (leader) {
-              issue_group(sl[phi], 0, phi, buf_open, phi == 0);
-              umma_commit(&empty[sl[phi]]);
-            }
-            __syncwarp();
+          if (leader) {
+            issue_group(ring_base + (uint32_t)slot * kB0Slab, wb, phi);
+            umma_commit(&empty[slot]);
           }
-          // conv_downsample of z row r into the same accumulators (K = 16 im2col chunk, one B per pool phase)
+          __syncwarp();
+          if (++slot == p.n_slots) { slot = 0; phase ^= 1; }
+        }
+        if (r <= 22) {
+          // conv_downsample of z row r into the row being started (slot g & 1): K = 16 im2col chunk against
+          // [0,B0,0,B1,0,B2,0] -- the zero blocks fall on the other slot's columns
           const int kq = nds % kB0NDS;
           { long long c0 = clock64(); mbar_wait(&dsfull[kq], (nds / kB0NDS) & 1); w_ds += clock64() - c0; }
           tc_fence_after_sync();
           if (leader) {
             const uint64_t a = b0_desc_noswz(ds_base + (uint32_t)(kq * kB0DsBytes));
-            const uint32_t d_tmem = tmem_base + (uint32_t)(buf_open * 96);      // columns [s0 | s1 | s2]
-            umma_f16(d_tmem, a, b0_desc_noswz(bds_addr), umma_idesc_f16(128, 96), 1);          // z_hi*w_hi + z_lo*w_hi
-            umma_f16(d_tmem, a, b0_desc_noswz(bds_addr + 3 * 1024), umma_idesc_f16(128, 96), 1);  // z_hi*w_lo
+            const uint32_t off = (g & 1) ? 0u : 1024u;
+            umma_f16(tmem_base, a, b0_desc_noswz(bds_addr + off), umma_idesc_f16(128, 192), 1);          // z_hi*w_hi + z_lo*w_hi
+            umma_f16(tmem_base, a, b0_desc_noswz(bds_addr + 7 * 1024 + off), umma_idesc_f16(128, 192), 1);   // z_hi*w_lo
             umma_commit(&dsempty[kq]);
           }
           __syncwarp();
           ++nds;
-        } else {
-          for (int phi = 0; phi < 3; ++phi) {
-            if (leader) umma_commit(&empty[sl[phi]]);
-            __syncwarp();
-          }
         }
-        for (int i = 0; i < 3; ++i) advance(slot, phase);
+        if (leader) umma_commit(&tfull[(g & 1) ^ 1]);
+        __syncwarp();
       }
     }
     if (p.stats && leader) {
@@ -253,36 +263,39 @@ block0_tc_kernel(const Block0Params p) {
     const int quad = warp & 3, half = (warp - 2) >> 2;
     const int m = quad * 32 + lane;                              // accumulator row
     const int col0 = half * 16;
-    float bias[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) bias[i] = __ldg(p.b2 + col0 + i);
-    int tcount = 0;
+    int tcount = 0;                        // completed conv2 steps (24 per strip; the first is the dummy row -1)
     for (int t = blockIdx.x; t < n_strips; t += gridDim.x) {
       const int jt = t % p.n_jt, b = t / p.n_jt;
       const int j = jt * kB0Strip + m;
       const bool store = m < kB0Strip && j / 3 < p.Jn;
       const bool valid = j < p.Wo;
-      for (int h = 0; h < 23; ++h, ++tcount) {
-        const int buf = tcount & 1;
-        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 96 + col0);
+      for (int h = -1; h < 23; ++h, ++tcount) {
+        const int buf = (tcount & 1) ^ 1;
+        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 32 + col0);
         mbar_wait(&tfull[buf], (tcount >> 1) & 1);
         tc_fence_after_sync();
         uint32_t acc[3][16];
+        if (h >= 0) {
 #pragma unroll
-        for (int s = 0; s < 3; ++s) tmem_ld16_async(t_row + (uint32_t)(s * 32), acc[s]);
+          for (int s = 0; s < 3; ++s) tmem_ld16_async(t_row + (uint32_t)(s * 64), acc[s]);
 #pragma unroll
-        for (int s = 0; s < 3; ++s) tmem_ld_wait16(acc[s]);
+          for (int s = 0; s < 3; ++s) tmem_ld_wait16(acc[s]);
+        }
+#pragma unroll
+        for (int s = 0; s < 3; ++s) tmem_st16_zero(t_row + (uint32_t)(s * 64));
+        tmem_st_wait();
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[buf]);
-        if (!store) continue;
+        if (!store || h < 0) continue;
         uint32_t hw[8], lw[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
+          const float2 bb = *reinterpret_cast<const float2*>(s_b2 + col0 + 2 * i);
           float x0 = fmaxf(fmaxf(__uint_as_float(acc[0][2 * i]), __uint_as_float(acc[1][2 * i])),
-                           __uint_as_float(acc[2][2 * i])) + bias[2 * i];
+                           __uint_as_float(acc[2][2 * i])) + bb.x;
           float x1 = fmaxf(fmaxf(__uint_as_float(acc[0][2 * i + 1]), __uint_as_float(acc[1][2 * i + 1])),
-                           __uint_as_float(acc[2][2 * i + 1])) + bias[2 * i + 1];
+                           __uint_as_float(acc[2][2 * i + 1])) + bb.y;
           if (!valid) { x0 = 0.f; x1 = 0.f; }
           b0_split2<false>(x0, x1, hw[i], lw[i]);
         }
@@ -506,9 +519,9 @@ int launch_block0_tc(aasist_handle* h, int sm_count, const uint8_t* wimg, const 
   p.z = z; p.out = out; p.wimg = wimg; p.b1 = b1; p.b2 = b2;
   p.B = nb; p.W = W; p.J = (W + 2) / 3; p.Wo = W / 3; p.Jn = (p.Wo + 2) / 3;
   p.n_jt = (std::max(p.J, 3 * p.Jn) + kB0Strip - 1) / kB0Strip;
-  const int fixed = 1024 + kB0ImgBytes + kB0NA1 * kB0A1Stride + kB0NDS * kB0DsBytes + 6 * kB0ZW * 2 + 512;
+  const int fixed = 1024 + kB0SmemImgBytes + kB0NA1 * kB0A1Stride + kB0NDS * kB0DsBytes + 6 * kB0ZW * 2 + 1024;
   p.n_slots = std::min(8, (227 * 1024 - fixed) / kB0Slab);
-  if (p.n_slots < 6) {
+  if (p.n_slots < 4) {
     set_error("block0_tc: shared memory budget allows only %d ring slots", p.n_slots);
     return AASIST_E_INVALID;
   }
