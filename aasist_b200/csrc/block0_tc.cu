@@ -87,9 +87,8 @@ block0_tc_kernel(const Block0Params p) {
   uint8_t* s_ring = smem + kB0SmemImgBytes;                    // v tiles
   uint8_t* s_a1 = s_ring + (size_t)p.n_slots * kB0Slab;        // conv1 im2col ring
   uint8_t* s_ds = s_a1 + kB0NA1 * kB0A1Stride;                 // downsample im2col ring
-  __half* s_zh = reinterpret_cast<__half*>(s_ds + kB0NDS * kB0DsBytes);   // [3][kB0ZW] rolling rows of z, hi halves
-  __half* s_zl = s_zh + 3 * kB0ZW;                                        // ... lo halves
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_zl + 3 * kB0ZW);
+  uint32_t* s_z = reinterpret_cast<uint32_t*>(s_ds + kB0NDS * kB0DsBytes);   // [3][kB0ZW] rolling rows of z as (hi,lo) fp16 words
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_z + 3 * kB0ZW);
   uint64_t* full = bars;                   // [8]  v tile written (8 transformer warps)
   uint64_t* empty = bars + 8;              // [8]  v tile consumed (tcgen05.commit)
   uint64_t* tfull = bars + 16;             // [2]  conv2 accumulators complete
@@ -168,13 +167,13 @@ block0_tc_kernel(const Block0Params p) {
     uint32_t phase = 0;
     int g2 = 0, nds = 0;                   // conv2 steps issued (step g starts an output row in slot g & 1)
     long long w_a1 = 0, w_d1 = 0, w_vf = 0, w_te = 0, w_ds = 0;
-    const long long t_begin = clock64();
+    const long long t_begin = AASIST_CLOCK();
 
     auto issue_conv1_row = [&]() {         // the three phase tiles of one v row
       for (int phi = 0; phi < 3; ++phi, ++n1) {
         const int ka = n1 % kB0NA1, kd = n1 % kB0ND1;
-        { long long c0 = clock64(); mbar_wait(&a1full[ka], (n1 / kB0NA1) & 1); w_a1 += clock64() - c0; }
-        { long long c0 = clock64(); mbar_wait(&d1empty[kd], ((n1 / kB0ND1) & 1) ^ 1); w_d1 += clock64() - c0; }
+        AASIST_TIMED_WAIT(&a1full[ka], (n1 / kB0NA1) & 1, w_a1);
+        AASIST_TIMED_WAIT(&d1empty[kd], ((n1 / kB0ND1) & 1) ^ 1, w_d1);
         tc_fence_after_sync();
         if (leader) {
           const uint64_t a = b0_desc_noswz(a1_base + (uint32_t)(ka * kB0A1Stride));
@@ -221,11 +220,11 @@ block0_tc_kernel(const Block0Params p) {
         if (r < 23) issue_conv1_row();                           // v row r+1 (one row ahead of conv2)
         // v row r: dh=1 completes output row r-1 (a dummy for r = 0, see block_fused_tc.cu), dh=0 starts row r
         const int g = g2++;
-        { long long c0 = clock64(); mbar_wait(&tempty[g & 1], (uint32_t)(((g - 1) >> 1) & 1)); w_te += clock64() - c0; }
+        AASIST_TIMED_WAIT(&tempty[g & 1], (uint32_t)(((g - 1) >> 1) & 1), w_te);
         tc_fence_after_sync();
         const uint32_t wb = w_base + (uint32_t)((g & 1) * kB0W2Bytes);
         for (int phi = 0; phi < 3; ++phi) {
-          { long long c0 = clock64(); mbar_wait(&full[slot], phase); w_vf += clock64() - c0; }
+          AASIST_TIMED_WAIT(&full[slot], phase, w_vf);
           tc_fence_after_sync();
           if (leader) {
             issue_group(ring_base + (uint32_t)slot * kB0Slab, wb, phi);
@@ -238,7 +237,7 @@ block0_tc_kernel(const Block0Params p) {
           // conv_downsample of z row r into the row being started (slot g & 1): K = 16 im2col chunk against
           // [0,B0,0,B1,0,B2,0] -- the zero blocks fall on the other slot's columns
           const int kq = nds % kB0NDS;
-          { long long c0 = clock64(); mbar_wait(&dsfull[kq], (nds / kB0NDS) & 1); w_ds += clock64() - c0; }
+          AASIST_TIMED_WAIT(&dsfull[kq], (nds / kB0NDS) & 1, w_ds);
           tc_fence_after_sync();
           if (leader) {
             const uint64_t a = b0_desc_noswz(ds_base + (uint32_t)(kq * kB0DsBytes));
@@ -256,7 +255,7 @@ block0_tc_kernel(const Block0Params p) {
     }
     if (p.stats && leader) {
       long long* st = p.stats + (size_t)blockIdx.x * 8;
-      st[0] = clock64() - t_begin; st[1] = w_a1; st[2] = w_d1; st[3] = w_vf; st[4] = w_te; st[5] = w_ds;
+      st[0] = AASIST_CLOCK() - t_begin; st[1] = w_a1; st[2] = w_d1; st[3] = w_vf; st[4] = w_te; st[5] = w_ds;
     }
   } else if (warp >= 2 && warp < 10) {
     // ======================================= epilogue =========================================
@@ -287,7 +286,11 @@ block0_tc_kernel(const Block0Params p) {
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[buf]);
+#ifdef B0_EXP_NO_EOUT
+        if (!store || h < 0 || acc[0][0] != 0x12345u) continue;
+#else
         if (!store || h < 0) continue;
+#endif
         uint32_t hw[8], lw[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -341,8 +344,13 @@ block0_tc_kernel(const Block0Params p) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const float2 bb = *reinterpret_cast<const float2*>(b1s + c * 16 + 2 * i);
+#ifdef B0_EXP_NO_TMATH
+                float x0 = __uint_as_float(acc[c][2 * i]) + bb.x;
+                float x1 = __uint_as_float(acc[c][2 * i + 1]) + bb.y;
+#else
                 float x0 = b0_selu(__uint_as_float(acc[c][2 * i]) + bb.x);
                 float x1 = b0_selu(__uint_as_float(acc[c][2 * i + 1]) + bb.y);
+#endif
                 if (!valid) { x0 = 0.f; x1 = 0.f; }
                 b0_split2<true>(x0, x1, hw[c * 8 + i], lw[c * 8 + i]);
               }
@@ -383,70 +391,76 @@ block0_tc_kernel(const Block0Params p) {
         }
       };
       auto store_row = [&](int row) {
-        __half* dh = s_zh + ((row + 3) % 3) * kB0ZW;
-        __half* dl = s_zl + ((row + 3) % 3) * kB0ZW;
+        uint32_t* d = s_z + ((row + 3) % 3) * kB0ZW;
 #pragma unroll
         for (int q = 0; q < PER; ++q) {
           const int c = ptid + 96 * q;
           if (c < kB0ZW) {
             const float v = fminf(fmaxf(pre[q], -65504.f), 65504.f);
             const __half hh = __float2half_rn(v);
-            dh[c] = hh;
-            dl[c] = __float2half_rn(v - __half2float(hh));
+            d[c] = pack_h2(hh, __float2half_rn(v - __half2float(hh)));
           }
         }
       };
-      // three consecutive halves starting at column c of a window row -> (h0,h1) word and (h2,0)
-      auto conv1_tile = [&](int r, int phi) {                    // v row r: z rows r-1, r (zero outside 0..22)
-        const int ka = n % kB0NA1;
-        mbar_wait(&a1empty[ka], ((n / kB0NA1) & 1) ^ 1);
-        uint8_t* dst = s_a1 + ka * kB0A1Stride;
-        const bool up = r >= 1 && r <= 23, dn = r <= 22;
-        const __half* uh = s_zh + ((r - 1 + 3) % 3) * kB0ZW;
-        const __half* ul = s_zl + ((r - 1 + 3) % 3) * kB0ZW;
-        const __half* nh = s_zh + (r % 3) * kB0ZW;
-        const __half* nl = s_zl + (r % 3) * kB0ZW;
-        const __half zero = __ushort_as_half((unsigned short)0);
-        for (int jj = ptid; jj < 136; jj += 96) {
-          const int c = min(3 * jj + phi, kB0ZW - 3);            // clamp only matters for discarded rows >= 128
-          __half h[6], l[6];
+      // One pass builds everything that depends on z rows q-1 ("up") and q ("dn"): the three conv1 im2col tiles
+      // of v row q (tile row jj, phase phi: taps at window columns 3jj+phi .. +2 of both rows) and the
+      // conv_downsample tile of output row q-1 (row m = jj-1: window columns 3jj .. 3jj+4 of the up row).
+      // A thread reads the five (hi,lo) words of each row once and permutes them into the K=16 operand rows
+      //   conv1: [up_hi(3) dn_hi(3) up_lo(3) dn_lo(3) 0(4)]      downsample: [z_hi(5) z_lo(5) 0(6)]
+      auto row_pass = [&](int q) {
+        const bool up = q >= 1, dn = q <= 22;
+        uint8_t* dst[3];
 #pragma unroll
-          for (int dw = 0; dw < 3; ++dw) {
-            h[dw] = up ? uh[c + dw] : zero;
-            l[dw] = up ? ul[c + dw] : zero;
-            h[3 + dw] = dn ? nh[c + dw] : zero;
-            l[3 + dw] = dn ? nl[c + dw] : zero;
+        for (int phi = 0; phi < 3; ++phi) {
+          const int ka = (n + phi) % kB0NA1;
+          mbar_wait(&a1empty[ka], (((n + phi) / kB0NA1) & 1) ^ 1);
+          dst[phi] = s_a1 + ka * kB0A1Stride;
+        }
+        uint8_t* dds = nullptr;
+        if (up) {
+          const int kq = nds % kB0NDS;
+          mbar_wait(&dsempty[kq], ((nds / kB0NDS) & 1) ^ 1);
+          dds = s_ds + kq * kB0DsBytes;
+        }
+        const uint32_t* zu = s_z + ((q - 1 + 3) % 3) * kB0ZW;
+        const uint32_t* zd = s_z + (q % 3) * kB0ZW;
+        for (int jj = ptid; jj < 129; jj += 96) {
+          uint32_t U[5], D[5];
+#pragma unroll
+          for (int i = 0; i < 5; ++i) {
+            U[i] = up ? zu[3 * jj + i] : 0u;
+            D[i] = dn ? zd[3 * jj + i] : 0u;
           }
-          uint8_t* row = dst + (jj >> 3) * 256 + (jj & 7) * 16;
-          *reinterpret_cast<uint4*>(row) =
-              make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(l[0], l[1]));
-          *reinterpret_cast<uint4*>(row + 128) = make_uint4(pack_h2(l[2], l[3]), pack_h2(l[4], l[5]), 0u, 0u);
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&a1full[ka]);
-        ++n;
-      };
-      auto ds_tile = [&](int h) {                                // output row h: z row h, taps 3j-1 .. 3j+3
-        const int kq = nds % kB0NDS;
-        mbar_wait(&dsempty[kq], ((nds / kB0NDS) & 1) ^ 1);
-        uint8_t* dst = s_ds + kq * kB0DsBytes;
-        const __half* zh = s_zh + (h % 3) * kB0ZW;
-        const __half* zl = s_zl + (h % 3) * kB0ZW;
-        for (int m = ptid; m < 128; m += 96) {
-          const int c = 3 * m + 3;                               // window column of position 3*(j0+m) - 1
-          __half hh[5], ll[5];
+          auto hh = [](uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x5410); };   // (a.hi, b.hi)
+          auto ll = [](uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x7632); };   // (a.lo, b.lo)
+          if (jj < 128) {
+            const uint32_t roff = (uint32_t)((jj >> 3) * 256 + (jj & 7) * 16);
 #pragma unroll
-          for (int i = 0; i < 5; ++i) { hh[i] = zh[c + i]; ll[i] = zl[c + i]; }
-          uint8_t* row = dst + (m >> 3) * 256 + (m & 7) * 16;
-          *reinterpret_cast<uint4*>(row) = make_uint4(pack_h2(hh[0], hh[1]), pack_h2(hh[2], hh[3]),
-                                                      pack_h2(hh[4], ll[0]), pack_h2(ll[1], ll[2]));
-          *reinterpret_cast<uint4*>(row + 128) = make_uint4(pack_h2(ll[3], ll[4]), 0u, 0u, 0u);
+            for (int phi = 0; phi < 3; ++phi) {
+              uint8_t* row = dst[phi] + roff;
+              *reinterpret_cast<uint4*>(row) = make_uint4(hh(U[phi], U[phi + 1]), hh(U[phi + 2], D[phi]),
+                                                          hh(D[phi + 1], D[phi + 2]), ll(U[phi], U[phi + 1]));
+              *reinterpret_cast<uint4*>(row + 128) =
+                  make_uint4(ll(U[phi + 2], D[phi]), ll(D[phi + 1], D[phi + 2]), 0u, 0u);
+            }
+          }
+          if (up && jj >= 1) {
+            const int m = jj - 1;
+            uint8_t* row = dds + (m >> 3) * 256 + (m & 7) * 16;
+            *reinterpret_cast<uint4*>(row) = make_uint4(hh(U[0], U[1]), hh(U[2], U[3]),
+                                                        __byte_perm(U[4], U[0], 0x7610), ll(U[1], U[2]));
+            *reinterpret_cast<uint4*>(row + 128) = make_uint4(ll(U[3], U[4]), 0u, 0u, 0u);
+          }
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&dsfull[kq]);
-        ++nds;
+        if (lane == 0) {
+#pragma unroll
+          for (int phi = 0; phi < 3; ++phi) mbar_arrive(&a1full[(n + phi) % kB0NA1]);
+          if (up) mbar_arrive(&dsfull[nds % kB0NDS]);
+        }
+        n += 3;
+        if (up) ++nds;
       };
       // same order as the MMA warp consumes: a1(row 0); then per r: a1(row r+1), ds(row r)
       asm volatile("bar.sync 3, 96;" ::: "memory");              // previous strip's window no longer read
@@ -454,16 +468,14 @@ block0_tc_kernel(const Block0Params p) {
       store_row(0);
       fetch_row(1);
       asm volatile("bar.sync 3, 96;" ::: "memory");
-      for (int phi = 0; phi < 3; ++phi) conv1_tile(0, phi);
-      for (int r = 0; r < 24; ++r) {
+      row_pass(0);
+      for (int r = 0; r < 23; ++r) {
         if (r < 22) {                                            // z row r+1 into the window, prefetch r+2
           store_row(r + 1);
           fetch_row(r + 2);
           asm volatile("bar.sync 3, 96;" ::: "memory");
         }
-        if (r < 23)
-          for (int phi = 0; phi < 3; ++phi) conv1_tile(r + 1, phi);
-        if (r <= 22) ds_tile(r);
+        row_pass(r + 1);                                         // conv1 tiles of v row r+1, downsample tile of row r
       }
     }
   }
@@ -530,6 +542,9 @@ int launch_block0_tc(aasist_handle* h, int sm_count, const uint8_t* wimg, const 
   const int grid = std::min(nb * p.n_jt, sm_count);
   static int want_stats = -1;
   if (want_stats < 0) { const char* e = getenv("AASIST_B0_STATS"); want_stats = e ? atoi(e) : 0; }
+#ifndef AASIST_KERNEL_STATS
+  want_stats = 0;   // the instrumentation is compiled in only by tools/variant_build.sh -DAASIST_KERNEL_STATS
+#endif
   p.stats = nullptr;
   if (want_stats) {
     AASIST_CUDA(cudaMalloc(&p.stats, sizeof(long long) * 8 * grid));

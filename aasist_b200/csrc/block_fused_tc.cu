@@ -166,7 +166,7 @@ block_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const BlockFusedP
     int vbase = 0;                         // global index of this strip's v row 0 (v row n lives in D1 slot n & 1)
     int g2 = 0;                            // conv2 steps issued (step g starts an output row in D2 slot g & 1)
     long long w_d1 = 0, w_x = 0, w_v = 0, w_t = 0;
-    const long long t_begin = clock64();
+    const long long t_begin = AASIST_CLOCK();
 
     // one A tile (128 rows x [hi|lo]) against `ntaps` merged column taps x both slots: N = 64 * ntaps,
     // three fp16 products, everything accumulates (the slots were zeroed when they were drained)
@@ -196,9 +196,7 @@ block_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const BlockFusedP
       }
     };
     auto d1_claim = [&](int n) {           // v row n is about to receive its first MMA: its slot must be drained
-      long long c0 = clock64();
-      mbar_wait(&d1empty[n & 1], ((n >> 1) & 1) ^ 1);
-      w_d1 += clock64() - c0;
+      AASIST_TIMED_WAIT(&d1empty[n & 1], ((n >> 1) & 1) ^ 1, w_d1);
     };
     auto conv1_step = [&](int h) {         // x row h: dh=1 completes v row h, dh=0 starts v row h+1
       const int n_old = vbase + h, n_new = n_old + 1;
@@ -207,7 +205,7 @@ block_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const BlockFusedP
       tc_fence_after_sync();
       const uint32_t wb = w1_base + (uint32_t)((n_new & 1) * kBfWBytes);   // order o: slot (n_new & 1) gets dh=0
       for (int phi = 0; phi < 3; ++phi) {
-        { long long c0 = clock64(); mbar_wait(&xfull[xslot], xphase); w_x += clock64() - c0; }
+        AASIST_TIMED_WAIT(&xfull[xslot], xphase, w_x);
         tc_fence_after_sync();
         if (leader) {
           issue_group(x_base + (uint32_t)xslot * kBfSlab, wb, phi, tmem_base + (uint32_t)D1_COL0);
@@ -225,11 +223,11 @@ block_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const BlockFusedP
     auto conv2_step = [&]() {              // v row r: dh=1 completes output row r-1, dh=0 starts output row r
       const int g = g2++;
       // slot g & 1 was last completed by step g-1 (the epilogue's (g-1)>>1-th drain of that slot); g = 0: none
-      { long long c0 = clock64(); mbar_wait(&tempty[g & 1], (uint32_t)(((g - 1) >> 1) & 1)); w_t += clock64() - c0; }
+      AASIST_TIMED_WAIT(&tempty[g & 1], (uint32_t)(((g - 1) >> 1) & 1), w_t);
       tc_fence_after_sync();
       const uint32_t wb = w2_base + (uint32_t)((g & 1) * kBfWBytes);
       for (int phi = 0; phi < 3; ++phi) {
-        { long long c0 = clock64(); mbar_wait(&vfull[vslot], vphase); w_v += clock64() - c0; }
+        AASIST_TIMED_WAIT(&vfull[vslot], vphase, w_v);
         tc_fence_after_sync();
         if (leader) {
           issue_group(v_base + (uint32_t)vslot * kBfSlab, wb, phi, tmem_base);
@@ -254,7 +252,7 @@ block_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const BlockFusedP
     }
     if (p.stats && leader) {
       long long* stt = p.stats + (size_t)blockIdx.x * 16;
-      stt[0] = clock64() - t_begin; stt[1] = w_d1; stt[2] = w_x; stt[3] = w_v; stt[4] = w_t;
+      stt[0] = AASIST_CLOCK() - t_begin; stt[1] = w_d1; stt[2] = w_x; stt[3] = w_v; stt[4] = w_t;
     }
   } else if (warp >= 2 && warp < 10) {
     // ======================================= epilogue =========================================
@@ -434,6 +432,9 @@ int launch_block_fused_tc(aasist_handle* h, int sm_count, const char* name, cons
   const int grid = std::min(nb * p.n_jt, sm_count);
   static int want_stats = -1;
   if (want_stats < 0) { const char* e = getenv("AASIST_BF_STATS"); want_stats = e ? atoi(e) : 0; }
+#ifndef AASIST_KERNEL_STATS
+  want_stats = 0;   // the instrumentation is compiled in only by tools/variant_build.sh -DAASIST_KERNEL_STATS
+#endif
   p.stats = nullptr;
   if (want_stats) {
     AASIST_CUDA(cudaMalloc(&p.stats, sizeof(long long) * 16 * grid));

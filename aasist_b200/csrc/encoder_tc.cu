@@ -266,7 +266,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t ring_base = smem_u32(s_ring);
     const bool leader = elect_one();
     long long w_te = 0, w_fu = 0;
-    const long long t_begin = clock64();
+    const long long t_begin = AASIST_CLOCK();
 
     // All MMAs of one input tile (phase phi) for tap row dh into accumulator buffer `buf`.
     // Pool phase s is served by tap dw with (s + dw - 1) == phi (mod 3), from A rows shifted by
@@ -315,7 +315,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     };
     auto begin_row = [&]() -> int {       // claim the next accumulator buffer (waits for its drain)
       const int buf = nstart & 1;
-      { long long c0 = clock64(); mbar_wait(&tempty[buf], ((nstart >> 1) & 1) ^ 1); w_te += clock64() - c0; }
+      AASIST_TIMED_WAIT(&tempty[buf], ((nstart >> 1) & 1) ^ 1, w_te);
       tc_fence_after_sync();
       ++nstart;
       return buf;
@@ -339,7 +339,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (two_pass) {
           if (o1_fresh) buf_open = begin_row();
           for (int phi = 0; phi < 3; ++phi) {
-            { long long c0 = clock64(); mbar_wait(&full[sl[phi]], ph[phi]); w_fu += clock64() - c0; }
+            AASIST_TIMED_WAIT(&full[sl[phi]], ph[phi], w_fu);
             tc_fence_after_sync();
             if (has_o1 && leader) issue_group(sl[phi], 1, phi, buf_open, o1_fresh && phi == 0, false);
             __syncwarp();
@@ -367,7 +367,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           int buf_new = -1;
           if (o1_fresh) buf_open = begin_row();
           for (int phi = 0; phi < 3; ++phi) {
-            { long long c0 = clock64(); mbar_wait(&full[sl[phi]], ph[phi]); w_fu += clock64() - c0; }
+            AASIST_TIMED_WAIT(&full[sl[phi]], ph[phi], w_fu);
             tc_fence_after_sync();
             if (has_o1 && leader) issue_group(sl[phi], 1, phi, buf_open, o1_fresh && phi == 0, false);
             __syncwarp();
@@ -387,7 +387,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int i = 0; i < 3; ++i) advance(slot, phase);
         if (HAS_SIDE && has_o0) {
           for (int phi = 0; phi < 3; ++phi) {
-            { long long c0 = clock64(); mbar_wait(&full[slot], phase); w_fu += clock64() - c0; }
+            AASIST_TIMED_WAIT(&full[slot], phase, w_fu);
             tc_fence_after_sync();
             if (leader) {
               issue_group(slot, 0, phi, buf_open, false, true);
@@ -405,7 +405,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     if (p.stats && leader) {
       long long* stt = p.stats + (size_t)blockIdx.x * 4;
-      stt[0] = clock64() - t_begin; stt[1] = w_fu; stt[2] = w_te;
+      stt[0] = AASIST_CLOCK() - t_begin; stt[1] = w_fu; stt[2] = w_te;
     }
   } else if (warp < 2 + kEpiWarps) {
     // =============================== epilogue (warps 2..9) ========================
@@ -809,6 +809,9 @@ static int launch_conv(aasist_handle* h, const char* name, const CUtensorMap& tm
   const int grid = std::min(n_strips, h->tc->sm_count);
   static int want_stats = -1;
   if (want_stats < 0) { const char* e = getenv("AASIST_TC_STATS"); want_stats = e ? atoi(e) : 0; }
+#ifndef AASIST_KERNEL_STATS
+  want_stats = 0;   // the instrumentation is compiled in only by tools/variant_build.sh -DAASIST_KERNEL_STATS
+#endif
   p.stats = nullptr;
   if (want_stats) {
     AASIST_CUDA(cudaMalloc(&p.stats, sizeof(long long) * 4 * grid));

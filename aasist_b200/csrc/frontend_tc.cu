@@ -170,14 +170,14 @@ sinc_frontend_tc_kernel(const FrontTcParams p) {
     constexpr uint32_t IDESC = umma_idesc_f16(128, kFtN);
     int tcount = 0;
     long long w_te = 0, w_af = 0;
-    const long long t_begin = clock64();
+    const long long t_begin = AASIST_CLOCK();
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
       const int buf = tcount & 1;
-      { long long c0 = clock64(); mbar_wait(&tempty[buf], ((tcount >> 1) & 1) ^ 1); w_te += clock64() - c0; }
+      AASIST_TIMED_WAIT(&tempty[buf], ((tcount >> 1) & 1) ^ 1, w_te);
       tc_fence_after_sync();
       const uint32_t d = tmem_base + (uint32_t)(buf * kFtBufCols);
       for (int kc = 0; kc < kFtKC; ++kc) {
-        { long long c0 = clock64(); mbar_wait(&afull[kc], tcount & 1); w_af += clock64() - c0; }
+        AASIST_TIMED_WAIT(&afull[kc], tcount & 1, w_af);
         tc_fence_after_sync();
         if (leader) {
           const uint64_t a_hi = umma_desc_noswz(a_base + (uint32_t)((2 * kc) * kFtAChunk));
@@ -196,7 +196,7 @@ sinc_frontend_tc_kernel(const FrontTcParams p) {
     }
     if (p.stats && leader) {
       long long* stt = p.stats + (size_t)blockIdx.x * 4;
-      stt[0] = clock64() - t_begin; stt[1] = w_af; stt[2] = w_te;
+      stt[0] = AASIST_CLOCK() - t_begin; stt[1] = w_af; stt[2] = w_te;
     }
   } else if (warp >= 2 && warp < 10) {
     // =============================== epilogue ====================================
@@ -327,6 +327,9 @@ int launch_frontend_tc(aasist_handle* h, const uint8_t* bimg, int sm_count, cons
   const int grid = std::min(B * p.n_tiles_per_utt, sm_count);
   static int want_stats = -1;
   if (want_stats < 0) { const char* e = getenv("AASIST_TC_STATS"); want_stats = e ? atoi(e) : 0; }
+#ifndef AASIST_KERNEL_STATS
+  want_stats = 0;   // the instrumentation is compiled in only by tools/variant_build.sh -DAASIST_KERNEL_STATS
+#endif
   p.stats = nullptr;
   if (want_stats) {
     AASIST_CUDA(cudaMalloc(&p.stats, sizeof(long long) * 4 * grid));

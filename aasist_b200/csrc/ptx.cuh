@@ -44,6 +44,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Wait-time instrumentation of the MMA-issuing warps (AASIST_*_STATS): compiled in only with
+// -DAASIST_KERNEL_STATS (tools/variant_build.sh) -- reading the clock around every wait costs the issuing
+// warp ~1000 cycles per output row, which the product build does not pay.
+#ifdef AASIST_KERNEL_STATS
+#define AASIST_TIMED_WAIT(bar, parity, acc) \
+  do { const long long c0_ = clock64(); mbar_wait(bar, parity); (acc) += clock64() - c0_; } while (0)
+#define AASIST_CLOCK() clock64()
+#else
+#define AASIST_TIMED_WAIT(bar, parity, acc) mbar_wait(bar, parity)
+#define AASIST_CLOCK() 0ll
+#endif
+
 // wait with sleep back-off: for warps that have slack (epilogue, operand producers) and share
 // an SMSP with math warps -- a sleeping warp issues nothing, a polling one steals issue slots
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
