@@ -157,7 +157,10 @@ block0_tc_kernel(const Block0Params p) {
 
   if (warp == 1) {
     // ======================================= MMA issuer =======================================
+    // the whole schedule runs in ONE elected lane: tcgen05.mma / tcgen05.commit are single-thread instructions
+    // and a single-lane loop pays neither divergence nor __syncwarp per step
     const bool leader = elect_one();
+    if (leader) {
     const uint32_t w_base = smem_u32(s_w), ring_base = smem_u32(s_ring);
     const uint32_t a1_base = smem_u32(s_a1), ds_base = smem_u32(s_ds);
     const uint32_t b1_addr = w_base + 2 * kB0W2Bytes, b1p_addr = b1_addr + 1024, bds_addr = b1_addr + 2048;
@@ -175,7 +178,7 @@ block0_tc_kernel(const Block0Params p) {
         AASIST_TIMED_WAIT(&a1full[ka], (n1 / kB0NA1) & 1, w_a1);
         AASIST_TIMED_WAIT(&d1empty[kd], ((n1 / kB0ND1) & 1) ^ 1, w_d1);
         tc_fence_after_sync();
-        if (leader) {
+        {
           const uint64_t a = b0_desc_noswz(a1_base + (uint32_t)(ka * kB0A1Stride));
           const uint32_t d = tmem_base + (uint32_t)(D1_COL0 + 32 * kd);
           umma_f16(d, a, b0_desc_noswz(b1_addr), IDESC, 0);
@@ -183,7 +186,6 @@ block0_tc_kernel(const Block0Params p) {
           umma_commit(&a1empty[ka]);
           umma_commit(&d1full[kd]);
         }
-        __syncwarp();
       }
     };
     // conv2 MMAs of one v tile.  Pool phases that read the same A rows share one wider-N MMA, and so do the
@@ -226,12 +228,11 @@ block0_tc_kernel(const Block0Params p) {
         for (int phi = 0; phi < 3; ++phi) {
           AASIST_TIMED_WAIT(&full[slot], phase, w_vf);
           tc_fence_after_sync();
-          if (leader) {
+          {
             issue_group(ring_base + (uint32_t)slot * kB0Slab, wb, phi);
             umma_commit(&empty[slot]);
           }
-          __syncwarp();
-          if (++slot == p.n_slots) { slot = 0; phase ^= 1; }
+            if (++slot == p.n_slots) { slot = 0; phase ^= 1; }
         }
         if (r <= 22) {
           // conv_downsample of z row r into the row being started (slot g & 1): K = 16 im2col chunk against
@@ -239,23 +240,22 @@ block0_tc_kernel(const Block0Params p) {
           const int kq = nds % kB0NDS;
           AASIST_TIMED_WAIT(&dsfull[kq], (nds / kB0NDS) & 1, w_ds);
           tc_fence_after_sync();
-          if (leader) {
+          {
             const uint64_t a = b0_desc_noswz(ds_base + (uint32_t)(kq * kB0DsBytes));
             const uint32_t off = (g & 1) ? 0u : 1024u;
             umma_f16(tmem_base, a, b0_desc_noswz(bds_addr + off), umma_idesc_f16(128, 192), 1);          // z_hi*w_hi + z_lo*w_hi
             umma_f16(tmem_base, a, b0_desc_noswz(bds_addr + 7 * 1024 + off), umma_idesc_f16(128, 192), 1);   // z_hi*w_lo
             umma_commit(&dsempty[kq]);
           }
-          __syncwarp();
-          ++nds;
+            ++nds;
         }
-        if (leader) umma_commit(&tfull[(g & 1) ^ 1]);
-        __syncwarp();
+        umma_commit(&tfull[(g & 1) ^ 1]);
       }
     }
-    if (p.stats && leader) {
+    if (p.stats) {
       long long* st = p.stats + (size_t)blockIdx.x * 8;
       st[0] = AASIST_CLOCK() - t_begin; st[1] = w_a1; st[2] = w_d1; st[3] = w_vf; st[4] = w_te; st[5] = w_ds;
+    }
     }
   } else if (warp >= 2 && warp < 10) {
     // ======================================= epilogue =========================================

@@ -158,7 +158,10 @@ block_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const BlockFusedP
     }
   } else if (warp == 1) {
     // ======================================= MMA issuer =======================================
+    // the whole schedule runs in ONE elected lane: tcgen05.mma / tcgen05.commit are single-thread instructions
+    // and a single-lane loop pays neither divergence nor __syncwarp per step
     const bool leader = elect_one();
+    if (leader) {
     const uint32_t w1_base = smem_u32(s_w1), w2_base = smem_u32(s_w2);
     const uint32_t v_base = smem_u32(s_v), x_base = smem_u32(s_x);
     int xslot = 0, vslot = 0;
@@ -207,18 +210,16 @@ block_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const BlockFusedP
       for (int phi = 0; phi < 3; ++phi) {
         AASIST_TIMED_WAIT(&xfull[xslot], xphase, w_x);
         tc_fence_after_sync();
-        if (leader) {
+        {
           issue_group(x_base + (uint32_t)xslot * kBfSlab, wb, phi, tmem_base + (uint32_t)D1_COL0);
           umma_commit(&xempty[xslot]);
         }
-        __syncwarp();
         if (++xslot == p.n_xslots) { xslot = 0; xphase ^= 1; }
       }
-      if (leader) {
+      {
         umma_commit(&d1full[n_old & 1]);
         if (h == 22) umma_commit(&d1full[n_new & 1]);                // v row 23 has no dh=1 contribution
       }
-      __syncwarp();
     };
     auto conv2_step = [&]() {              // v row r: dh=1 completes output row r-1, dh=0 starts output row r
       const int g = g2++;
@@ -229,17 +230,15 @@ block_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const BlockFusedP
       for (int phi = 0; phi < 3; ++phi) {
         AASIST_TIMED_WAIT(&vfull[vslot], vphase, w_v);
         tc_fence_after_sync();
-        if (leader) {
+        {
           issue_group(v_base + (uint32_t)vslot * kBfSlab, wb, phi, tmem_base);
           umma_commit(&vempty[vslot]);
         }
-        __syncwarp();
         if (++vslot == p.n_vslots) { vslot = 0; vphase ^= 1; }
       }
       // the row in the other slot is complete.  For v row 0 that "row" is a dummy (output row -1: it holds the
       // dh=0 product of the previous strip's v row 23 plus this dh=1 product); the epilogue just clears it.
-      if (leader) umma_commit(&tfull[(g & 1) ^ 1]);
-      __syncwarp();
+      umma_commit(&tfull[(g & 1) ^ 1]);
     };
 
     for (int t = blockIdx.x; t < n_strips; t += gridDim.x) {
@@ -250,9 +249,10 @@ block_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const BlockFusedP
       }
       vbase += 24;
     }
-    if (p.stats && leader) {
+    if (p.stats) {
       long long* stt = p.stats + (size_t)blockIdx.x * 16;
       stt[0] = AASIST_CLOCK() - t_begin; stt[1] = w_d1; stt[2] = w_x; stt[3] = w_v; stt[4] = w_t;
+    }
     }
   } else if (warp >= 2 && warp < 10) {
     // ======================================= epilogue =========================================
