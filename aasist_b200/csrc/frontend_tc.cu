@@ -165,7 +165,8 @@ sinc_frontend_tc_kernel(const FrontTcParams p) {
 
   if (warp == 1) {
     // =============================== MMA issuer ==================================
-    const bool leader = elect_one();
+    const bool leader = elect_one();   // the whole schedule runs in this one lane
+    if (leader) {
     const uint32_t a_base = smem_u32(s_a), b_base = smem_u32(s_b);
     constexpr uint32_t IDESC = umma_idesc_f16(128, kFtN);
     int tcount = 0;
@@ -179,7 +180,7 @@ sinc_frontend_tc_kernel(const FrontTcParams p) {
       for (int kc = 0; kc < kFtKC; ++kc) {
         AASIST_TIMED_WAIT(&afull[kc], tcount & 1, w_af);
         tc_fence_after_sync();
-        if (leader) {
+        {
           const uint64_t a_hi = umma_desc_noswz(a_base + (uint32_t)((2 * kc) * kFtAChunk));
           const uint64_t a_lo = umma_desc_noswz(a_base + (uint32_t)((2 * kc + 1) * kFtAChunk));
           const uint64_t b_hi = umma_desc_noswz(b_base + (uint32_t)(kc * kFtBChunk));
@@ -189,14 +190,13 @@ sinc_frontend_tc_kernel(const FrontTcParams p) {
           umma_f16(d, a_hi, b_lo, IDESC, 1);
           umma_commit(&aempty[kc]);
         }
-        __syncwarp();
       }
-      if (leader) umma_commit(&tfull[buf]);
-      __syncwarp();
+      umma_commit(&tfull[buf]);
     }
-    if (p.stats && leader) {
+    if (p.stats) {
       long long* stt = p.stats + (size_t)blockIdx.x * 4;
       stt[0] = AASIST_CLOCK() - t_begin; stt[1] = w_af; stt[2] = w_te;
+    }
     }
   } else if (warp >= 2 && warp < 10) {
     // =============================== epilogue ====================================
