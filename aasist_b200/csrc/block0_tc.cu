@@ -59,10 +59,12 @@ __device__ __forceinline__ float b0_ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float b0_selu(float v) {
-  const float e = b0_ex2(v * 1.4426950408889634f);
+// SELU of v given y = v * log2(e) (conv1's weights and bias are pre-scaled by log2(e) on the host, and the
+// bias rides in the MMA as a constant-1 im2col column): one MUFU.EX2 and five FMA-pipe instructions
+__device__ __forceinline__ float b0_selu_scaled(float y) {
+  const float e = b0_ex2(y);
   const float n = fminf(fmaf(e, kSeluScale * kSeluAlpha, -(kSeluScale * kSeluAlpha)), 0.f);
-  return fmaf(fmaxf(v, 0.f), kSeluScale, n);
+  return fmaf(fmaxf(y, 0.f), kSeluScale * 0.6931471805599453f, n);
 }
 template <bool LOWER_BOUNDED>
 __device__ __forceinline__ void b0_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
@@ -315,12 +317,13 @@ block0_tc_kernel(const Block0Params p) {
     const int jj = quad * 32 + lane;                             // tile row
     const uint32_t row_off = (uint32_t)jj * 128;
     const uint32_t sw = (uint32_t)(jj & 7);
-    const float* b1s = s_b1;
     int n = 0, slot = 0;
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < n_strips; t += gridDim.x) {
       const int jt = t % p.n_jt;
       const int j = jt * kB0Strip - 1 + jj;
+      // warp-uniform: every row of this warp lies inside [0, W) for all three phases
+      const bool valid_all = jt * kB0Strip - 1 + quad * 32 >= 0 && 3 * (jt * kB0Strip - 1 + quad * 32 + 31) + 2 < p.W;
       for (int r = 0; r < 24; ++r) {
         for (int phi = 0; phi < 3; ++phi, ++n) {
           if ((n & 1) == grp) {
@@ -339,21 +342,24 @@ block0_tc_kernel(const Block0Params p) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&d1empty[kd]);
             uint32_t hw[16], lw[16];
+            if (valid_all) {                                     // interior strip: no zero-padding mask needed
 #pragma unroll
-            for (int c = 0; c < 2; ++c)
+              for (int c = 0; c < 2; ++c)
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float2 bb = *reinterpret_cast<const float2*>(b1s + c * 16 + 2 * i);
-#ifdef B0_EXP_NO_TMATH
-                float x0 = __uint_as_float(acc[c][2 * i]) + bb.x;
-                float x1 = __uint_as_float(acc[c][2 * i + 1]) + bb.y;
-#else
-                float x0 = b0_selu(__uint_as_float(acc[c][2 * i]) + bb.x);
-                float x1 = b0_selu(__uint_as_float(acc[c][2 * i + 1]) + bb.y);
-#endif
-                if (!valid) { x0 = 0.f; x1 = 0.f; }
-                b0_split2<true>(x0, x1, hw[c * 8 + i], lw[c * 8 + i]);
-              }
+                for (int i = 0; i < 8; ++i)
+                  b0_split2<true>(b0_selu_scaled(__uint_as_float(acc[c][2 * i])),
+                                  b0_selu_scaled(__uint_as_float(acc[c][2 * i + 1])), hw[c * 8 + i], lw[c * 8 + i]);
+            } else {
+#pragma unroll
+              for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  float x0 = b0_selu_scaled(__uint_as_float(acc[c][2 * i]));
+                  float x1 = b0_selu_scaled(__uint_as_float(acc[c][2 * i + 1]));
+                  if (!valid) { x0 = 0.f; x1 = 0.f; }
+                  b0_split2<true>(x0, x1, hw[c * 8 + i], lw[c * 8 + i]);
+                }
+            }
             mbar_wait(&empty[slot], phase ^ 1);
             uint8_t* row = s_ring + (size_t)slot * kB0Slab + row_off;
 #pragma unroll
@@ -406,7 +412,7 @@ block0_tc_kernel(const Block0Params p) {
       // of v row q (tile row jj, phase phi: taps at window columns 3jj+phi .. +2 of both rows) and the
       // conv_downsample tile of output row q-1 (row m = jj-1: window columns 3jj .. 3jj+4 of the up row).
       // A thread reads the five (hi,lo) words of each row once and permutes them into the K=16 operand rows
-      //   conv1: [up_hi(3) dn_hi(3) up_lo(3) dn_lo(3) 0(4)]      downsample: [z_hi(5) z_lo(5) 0(6)]
+      //   conv1: [up_hi(3) dn_hi(3) up_lo(3) dn_lo(3) 1 0(3)]    downsample: [z_hi(5) z_lo(5) 0(6)]
       auto row_pass = [&](int q) {
         const bool up = q >= 1, dn = q <= 22;
         uint8_t* dst[3];
@@ -441,7 +447,7 @@ block0_tc_kernel(const Block0Params p) {
               *reinterpret_cast<uint4*>(row) = make_uint4(hh(U[phi], U[phi + 1]), hh(U[phi + 2], D[phi]),
                                                           hh(D[phi + 1], D[phi + 2]), ll(U[phi], U[phi + 1]));
               *reinterpret_cast<uint4*>(row + 128) =
-                  make_uint4(ll(U[phi + 2], D[phi]), ll(D[phi + 1], D[phi + 2]), 0u, 0u);
+                  make_uint4(ll(U[phi + 2], D[phi]), ll(D[phi + 1], D[phi + 2]), 0x00003C00u, 0u);   // k = 12: 1.0 (bias)
             }
           }
           if (up && jj >= 1) {
@@ -501,12 +507,17 @@ static void put_k16(std::vector<uint8_t>& img, size_t base, int n, int k, float 
 
 // image = [conv2 weights (built by the caller, kB0W2Bytes)] [B1] [B1'] [Bds(s), Bds'(s)] x 3
 void block0_pack_small(std::vector<uint8_t>& img, const std::vector<float>& w1 /*[6][32] bn folded*/,
-                       const std::vector<float>& wd /*[3][32]*/, int co) {
+                       const std::vector<float>& wd /*[3][32]*/, const std::vector<float>& bias1 /*[32] bn folded*/,
+                       int co) {
   img.resize(kB0ImgBytes, 0);
   const size_t b1 = kB0W2Bytes, b1p = b1 + 1024, bds = b1 + 2048;
   for (int o = 0; o < co; ++o) {
+    // conv1 and its bias are scaled by log2(e): the transformers evaluate SELU from y = v * log2(e)
+    const float bl = (float)((double)bias1[o] * 1.4426950408889634);
+    put_k16(img, b1, o, 12, bl, false);         // constant-1 column x bias_hi
+    put_k16(img, b1p, o, 12, bl, true);         //                   x bias_lo
     for (int tp = 0; tp < 6; ++tp) {
-      const float w = w1[tp * 32 + o];
+      const float w = (float)((double)w1[tp * 32 + o] * 1.4426950408889634);
       put_k16(img, b1, o, tp, w, false);        // z_hi taps  x w_hi
       put_k16(img, b1, o, 6 + tp, w, false);    // z_lo taps  x w_hi
       put_k16(img, b1p, o, tp, w, true);        // z_hi taps  x w_lo

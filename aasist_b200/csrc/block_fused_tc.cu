@@ -55,10 +55,12 @@ __device__ __forceinline__ float bf_ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float bf_selu(float v) {
-  const float e = bf_ex2(v * 1.4426950408889634f);
+// SELU of v given y = v * log2(e): conv1's weights and bias are pre-scaled by log2(e) on the host and the bias
+// is what the conv1 accumulators start from (the transformers store it back when they drain a slot)
+__device__ __forceinline__ float bf_selu_scaled(float y) {
+  const float e = bf_ex2(y);
   const float n = fminf(fmaf(e, kSeluScale * kSeluAlpha, -(kSeluScale * kSeluAlpha)), 0.f);
-  return fmaf(fmaxf(v, 0.f), kSeluScale, n);
+  return fmaf(fmaxf(y, 0.f), kSeluScale * 0.6931471805599453f, n);
 }
 template <bool LOWER_BOUNDED>
 __device__ __forceinline__ void bf_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
@@ -129,10 +131,22 @@ block_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const BlockFusedP
   const uint32_t tmem_base = *tmem_ptr;
   // TMEM: [0,192) conv2 accumulators, [192,384) conv1 accumulators; column = s*64 + slot*32 + channel
   constexpr int D1_COL0 = 192;
-  if (warp >= 2) {                         // accumulators start at zero (and return to zero after every drain)
-    const uint32_t tz = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(((warp - 2) >> 2) * 96);
+  if (warp >= 2) {   // conv2 accumulators start at zero, conv1 accumulators at the bias (and return there after every drain)
+    const int part = (warp - 2) >> 2;      // 0,1: D2 halves; 2,3: D1 halves
+    const uint32_t tz = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(part * 96);
+    if (part < 2) {
 #pragma unroll
-    for (int c = 0; c < 6; ++c) tmem_st16_zero(tz + (uint32_t)(c * 16));
+      for (int c = 0; c < 6; ++c) tmem_st16_zero(tz + (uint32_t)(c * 16));
+    } else {
+      uint32_t bb[2][16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        bb[0][i] = __float_as_uint(s_b1[i]);
+        bb[1][i] = __float_as_uint(s_b1[16 + i]);
+      }
+#pragma unroll
+      for (int c = 0; c < 6; ++c) tmem_st16(tz + (uint32_t)(c * 16), bb[c & 1]);   // 32-column [slot] blocks
+    }
     tmem_st_wait();
   }
   tc_fence_before_sync();
@@ -361,6 +375,8 @@ block_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const BlockFusedP
     for (int t = blockIdx.x; t < n_strips; t += gridDim.x) {
       const int jt = t % p.n_jt;
       const int j = jt * kBfStrip - 1 + jj;
+      // warp-uniform: every row of this warp lies inside [0, W) for all three phases
+      const bool valid_all = jt * kBfStrip - 1 + quad * 32 >= 0 && 3 * (jt * kBfStrip - 1 + quad * 32 + 31) + 2 < p.W;
       for (int r = 0; r < 24; ++r, ++nrow) {
         const int buf = nrow & 1;
         const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(D1_COL0 + buf * 32 + col0);
@@ -371,23 +387,37 @@ block_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const BlockFusedP
         for (int s = 0; s < 3; ++s) tmem_ld16_async(ta + (uint32_t)(s * 64), acc[s]);
 #pragma unroll
         for (int s = 0; s < 3; ++s) tmem_ld_wait16(acc[s]);
+        {
+          uint32_t bb[16];
 #pragma unroll
-        for (int s = 0; s < 3; ++s) tmem_st16_zero(ta + (uint32_t)(s * 64));
+          for (int i = 0; i < 4; ++i) {
+            const uint4 q = *reinterpret_cast<const uint4*>(s_b1 + col0 + 4 * i);
+            bb[4 * i] = q.x; bb[4 * i + 1] = q.y; bb[4 * i + 2] = q.z; bb[4 * i + 3] = q.w;
+          }
+#pragma unroll
+          for (int s = 0; s < 3; ++s) tmem_st16(ta + (uint32_t)(s * 64), bb);
+        }
         tmem_st_wait();
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&d1empty[buf]);
 #pragma unroll
         for (int s = 0; s < 3; ++s) {
-          const bool valid = j >= 0 && 3 * j + s < p.W;            // conv2 zero-pads v itself
           uint32_t hw[8], lw[8];
+          if (valid_all) {                                         // interior strip: no zero-padding mask needed
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float2 bb = *reinterpret_cast<const float2*>(s_b1 + col0 + 2 * i);
-            float x0 = bf_selu(__uint_as_float(acc[s][2 * i]) + bb.x);
-            float x1 = bf_selu(__uint_as_float(acc[s][2 * i + 1]) + bb.y);
-            if (!valid) { x0 = 0.f; x1 = 0.f; }
-            bf_split2<true>(x0, x1, hw[i], lw[i]);
+            for (int i = 0; i < 8; ++i)
+              bf_split2<true>(bf_selu_scaled(__uint_as_float(acc[s][2 * i])),
+                              bf_selu_scaled(__uint_as_float(acc[s][2 * i + 1])), hw[i], lw[i]);
+          } else {
+            const bool valid = j >= 0 && 3 * j + s < p.W;          // conv2 zero-pads v itself
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float x0 = bf_selu_scaled(__uint_as_float(acc[s][2 * i]));
+              float x1 = bf_selu_scaled(__uint_as_float(acc[s][2 * i + 1]));
+              if (!valid) { x0 = 0.f; x1 = 0.f; }
+              bf_split2<true>(x0, x1, hw[i], lw[i]);
+            }
           }
           mbar_wait(&vempty[slot], phase ^ 1);
           uint8_t* row = s_v + (size_t)slot * kBfSlab + row_off;

@@ -628,6 +628,8 @@ static int upload_f(float** dst, const std::vector<float>& v) {
 }
 
 static inline int pad_ch(int c) { return c <= 32 ? 32 : 64; }
+// blocks whose conv1 -> conv2 intermediate stays on chip in block_fused_tc.cu
+static inline bool is_fused_block(const BlockTc& b) { return !b.downsample && b.cpi == 32 && b.cop == 32; }
 
 static int pack_block_tc(aasist_handle* h, const std::string& pfx, int index, BlockTc& blk) {
   const int ci = h->cfg.enc_channels[index][0], co = h->cfg.enc_channels[index][1];
@@ -668,11 +670,16 @@ static int pack_block_tc(aasist_handle* h, const std::string& pfx, int index, Bl
   } else {
     const int tap_bytes = (blk.cpi / 32) * blk.cop * 128;
     std::vector<uint8_t> img((size_t)6 * tap_bytes, 0);
-    for (int o = 0; o < co; ++o)
+    // 32 -> 32 identity blocks run in block_fused_tc.cu, whose transformers evaluate SELU from
+    // y = v * log2(e): conv1 (and its bias, the accumulators' start value there) is pre-scaled
+    const double pre = is_fused_block(blk) ? 1.4426950408889634 : 1.0;
+    for (int o = 0; o < co; ++o) {
+      bias1[o] = (float)((double)bias1[o] * pre);
       for (int i = 0; i < ci; ++i)
         for (int t = 0; t < 6; ++t)
           put_tap(img, 0, blk.cpi, blk.cop, t / 3, t % 3, o, i,
-                  (float)((double)w1[((size_t)o * ci + i) * 6 + t] * sc[o]));
+                  (float)((double)w1[((size_t)o * ci + i) * 6 + t] * sc[o] * pre));
+    }
     blk.c1.wimg_bytes = (int)img.size();
     if ((rc = upload_bytes(&blk.c1.wimg, img))) return rc;
   }
@@ -703,7 +710,7 @@ static int pack_block_tc(aasist_handle* h, const std::string& pfx, int index, Bl
     if ((rc = upload_bytes(&blk.c2.wimg, img))) return rc;
     if (index == 0) {
       std::vector<uint8_t> img0 = img;            // conv2 taps first, then the small K=16 operands
-      block0_pack_small(img0, blk.w1_host, blk.wd_host, co);
+      block0_pack_small(img0, blk.w1_host, blk.wd_host, bias1, co);
       if ((rc = upload_bytes(&blk.b0_img, img0))) return rc;
     }
   }
@@ -859,7 +866,7 @@ static int run_block_tc(aasist_handle* h, int enc, int index, const __half* in_p
   // ---- block 0 and 32->32 identity blocks: the whole block is one kernel, intermediate kept on chip ----
   if (index == 0)
     return launch_block0_tc(h, h->tc->sm_count, blk.b0_img, blk.c1.bias, blk.c2.bias, z, nb, W, out_pairs, st);
-  if (!blk.downsample && blk.cpi == 32 && blk.cop == 32) {
+  if (is_fused_block(blk)) {
     static const char* names[6] = {"", "enc1.fused_tc", "enc2.fused_tc", "enc3.fused_tc", "enc4.fused_tc", "enc5.fused_tc"};
     return launch_block_fused_tc(h, h->tc->sm_count, names[index], tmIn, blk.c1.wimg, blk.c2.wimg, blk.c1.bias,
                                  blk.c2.bias, in_pairs, nb, W, blk.co, out_pairs, out_f32, st);

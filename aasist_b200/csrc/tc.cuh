@@ -20,7 +20,8 @@ int tc_front_finalize(aasist_handle* h, uint8_t** bimg_dev);
 int launch_frontend_tc(aasist_handle* h, const uint8_t* bimg, int sm_count, const float* x, int B, int L,
                        float* out, cudaStream_t st);
 // encoder block 0 fully on tensor cores (block0_tc.cu)
-void block0_pack_small(std::vector<uint8_t>& img, const std::vector<float>& w1, const std::vector<float>& wd, int co);
+void block0_pack_small(std::vector<uint8_t>& img, const std::vector<float>& w1, const std::vector<float>& wd,
+                       const std::vector<float>& bias1, int co);
 int block0_image_bytes();
 int block0_w2_bytes();
 int launch_block0_tc(aasist_handle* h, int sm_count, const uint8_t* wimg, const float* b1, const float* b2,
