@@ -98,7 +98,7 @@ block0_tc_kernel(const Block0Params p) {
   uint64_t* a1full = bars + 20;            // [kB0NA1]  (3 producer warps)
   uint64_t* a1empty = a1full + kB0NA1;     // [kB0NA1]
   uint64_t* d1full = a1empty + kB0NA1;     // [kB0ND1]  conv1 accumulator complete
-  uint64_t* d1empty = d1full + kB0ND1;     // [kB0ND1]  ... drained (4 transformer warps)
+  uint64_t* d1empty = d1full + kB0ND1;     // [kB0ND1]  ... drained (8 transformer warps)
   uint64_t* dsfull = d1empty + kB0ND1;     // [kB0NDS]
   uint64_t* dsempty = dsfull + kB0NDS;     // [kB0NDS]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(dsempty + kB0NDS);
@@ -133,10 +133,10 @@ block0_tc_kernel(const Block0Params p) {
   }
   fence_proxy_async_smem();
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 8; ++i) { mbar_init(&full[i], 4); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 8; ++i) { mbar_init(&full[i], 8); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
     for (int i = 0; i < kB0NA1; ++i) { mbar_init(&a1full[i], 3); mbar_init(&a1empty[i], 1); }
-    for (int i = 0; i < kB0ND1; ++i) { mbar_init(&d1full[i], 1); mbar_init(&d1empty[i], 4); }
+    for (int i = 0; i < kB0ND1; ++i) { mbar_init(&d1full[i], 1); mbar_init(&d1empty[i], 8); }
     for (int i = 0; i < kB0NDS; ++i) { mbar_init(&dsfull[i], 3); mbar_init(&dsempty[i], 1); }
     fence_barrier_init();
   }
@@ -310,13 +310,15 @@ block0_tc_kernel(const Block0Params p) {
       }
     }
   } else if (warp >= 10 && warp < 18) {
-    // ============ transformers: D1 (TMEM) -> bias, SELU, zero-pad mask, fp16 pairs -> swizzled v tile ============
-    // two groups of four warps (one warp per TMEM lane quadrant) take alternate tiles, so two tiles
-    // are in flight; a thread owns one tile row and all 32 channels.
-    const int quad = warp & 3, grp = (warp - 10) >> 2;
+    // ============ transformers: D1 (TMEM) -> SELU, zero-pad mask, fp16 pairs -> swizzled v tiles ============
+    // warp = (TMEM lane quadrant, 16-channel half).  A whole v row (three phase tiles) is handled at once: one
+    // wait, three tcgen05.ld, the D1 tiles released immediately, 48 SELUs per thread, one proxy fence.
+    const int quad = warp & 3, half = (warp - 10) >> 2;
     const int jj = quad * 32 + lane;                             // tile row
+    const int col0 = half * 16;
     const uint32_t row_off = (uint32_t)jj * 128;
     const uint32_t sw = (uint32_t)(jj & 7);
+    const uint32_t c_hi = (uint32_t)(2 * half), c_lo = (uint32_t)(4 + 2 * half);   // 16-byte chunks of this half
     int n = 0, slot = 0;
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < n_strips; t += gridDim.x) {
@@ -324,56 +326,58 @@ block0_tc_kernel(const Block0Params p) {
       const int j = jt * kB0Strip - 1 + jj;
       // warp-uniform: every row of this warp lies inside [0, W) for all three phases
       const bool valid_all = jt * kB0Strip - 1 + quad * 32 >= 0 && 3 * (jt * kB0Strip - 1 + quad * 32 + 31) + 2 < p.W;
-      for (int r = 0; r < 24; ++r) {
-        for (int phi = 0; phi < 3; ++phi, ++n) {
-          if ((n & 1) == grp) {
-            const int kd = n % kB0ND1;
-            const int pos = 3 * j + phi;
-            const bool valid = j >= 0 && pos < p.W;              // conv2 zero-pads v itself
-            mbar_wait(&d1full[kd], (n / kB0ND1) & 1);
-            tc_fence_after_sync();
-            uint32_t acc[2][16];
-            const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(D1_COL0 + 32 * kd);
-            tmem_ld16_async(ta, acc[0]);
-            tmem_ld16_async(ta + 16, acc[1]);
-            tmem_ld_wait16(acc[0]);
-            tmem_ld_wait16(acc[1]);
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&d1empty[kd]);
-            uint32_t hw[16], lw[16];
-            if (valid_all) {                                     // interior strip: no zero-padding mask needed
+      for (int r = 0; r < 24; ++r, n += 3) {
+        uint32_t acc[3][16];
+        {
+          const int kl = (n + 2) % kB0ND1;                       // commits arrive in order: the last tile's suffices
+          mbar_wait(&d1full[kl], ((n + 2) / kB0ND1) & 1);
+          tc_fence_after_sync();
 #pragma unroll
-              for (int c = 0; c < 2; ++c)
+          for (int s = 0; s < 3; ++s)
+            tmem_ld16_async(tmem_base + ((uint32_t)(quad * 32) << 16) +
+                                (uint32_t)(D1_COL0 + 32 * ((n + s) % kB0ND1) + col0), acc[s]);
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                  b0_split2<true>(b0_selu_scaled(__uint_as_float(acc[c][2 * i])),
-                                  b0_selu_scaled(__uint_as_float(acc[c][2 * i + 1])), hw[c * 8 + i], lw[c * 8 + i]);
-            } else {
+          for (int s = 0; s < 3; ++s) tmem_ld_wait16(acc[s]);
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) {
 #pragma unroll
-              for (int c = 0; c < 2; ++c)
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  float x0 = b0_selu_scaled(__uint_as_float(acc[c][2 * i]));
-                  float x1 = b0_selu_scaled(__uint_as_float(acc[c][2 * i + 1]));
-                  if (!valid) { x0 = 0.f; x1 = 0.f; }
-                  b0_split2<true>(x0, x1, hw[c * 8 + i], lw[c * 8 + i]);
-                }
-            }
-            mbar_wait(&empty[slot], phase ^ 1);
-            uint8_t* row = s_ring + (size_t)slot * kB0Slab + row_off;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {                        // chunks 0..3 = hi channels, 4..7 = lo channels
-              *reinterpret_cast<uint4*>(row + (((uint32_t)q ^ sw) << 4)) =
-                  make_uint4(hw[4 * q], hw[4 * q + 1], hw[4 * q + 2], hw[4 * q + 3]);
-              *reinterpret_cast<uint4*>(row + (((uint32_t)(4 + q) ^ sw) << 4)) =
-                  make_uint4(lw[4 * q], lw[4 * q + 1], lw[4 * q + 2], lw[4 * q + 3]);
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full[slot]);
+            for (int s = 0; s < 3; ++s) mbar_arrive(&d1empty[(n + s) % kB0ND1]);
           }
+        }
+        int sl[3];
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          uint32_t hw[8], lw[8];
+          if (valid_all) {                                       // interior strip: no zero-padding mask needed
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              b0_split2<true>(b0_selu_scaled(__uint_as_float(acc[s][2 * i])),
+                              b0_selu_scaled(__uint_as_float(acc[s][2 * i + 1])), hw[i], lw[i]);
+          } else {
+            const bool valid = j >= 0 && 3 * j + s < p.W;        // conv2 zero-pads v itself
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float x0 = b0_selu_scaled(__uint_as_float(acc[s][2 * i]));
+              float x1 = b0_selu_scaled(__uint_as_float(acc[s][2 * i + 1]));
+              if (!valid) { x0 = 0.f; x1 = 0.f; }
+              b0_split2<true>(x0, x1, hw[i], lw[i]);
+            }
+          }
+          mbar_wait(&empty[slot], phase ^ 1);
+          uint8_t* row = s_ring + (size_t)slot * kB0Slab + row_off;
+          *reinterpret_cast<uint4*>(row + ((c_hi ^ sw) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint4*>(row + (((c_hi + 1) ^ sw) << 4)) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+          *reinterpret_cast<uint4*>(row + ((c_lo ^ sw) << 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          *reinterpret_cast<uint4*>(row + (((c_lo + 1) ^ sw) << 4)) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+          sl[s] = slot;
           if (++slot == p.n_slots) { slot = 0; phase ^= 1; }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (int s = 0; s < 3; ++s) mbar_arrive(&full[sl[s]]);
         }
       }
     }
