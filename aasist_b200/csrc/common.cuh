@@ -73,6 +73,7 @@ struct PoolParams {  // GraphPool (AASIST.py:285-322)
 
 struct GraphArgsAasist {
   // dims
+  int B;             // utterances in this launch (a CTA walks b = blockIdx.x, blockIdx.x + gridDim.x, ...)
   int C, NT, g0, g1, nS, nT, nS2, nT2;
   int ld;            // smem row stride (floats), odd
   int nmax;          // max node count of any layer

@@ -6,6 +6,8 @@
 //   a8  HtrgGraphAttentionLayer         models/AASIST.py:150-282
 //   a9  branch fusion, readout, head    models/AASIST.py:865-921
 //   a11 RawGAT-ST graph tail            models/RawNetGatSpoofST.py:338-356
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace aasist {
@@ -351,7 +353,8 @@ aasist_graph_kernel(const GraphArgsAasist a) {
   float* m2 = bump(p, kMaxDim);
   float* m0 = bump(p, kMaxDim);
 
-  const int b = blockIdx.x;
+  // the grid is sized so that every CTA walks the same number of utterances (no partial last wave)
+  for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
   const float* e = a.e + (size_t)b * a.C * kSpecNodes * a.NT;
   int32_t* gi = a.topk_idx ? a.topk_idx + (size_t)b * a.topk_total : nullptr;
   float* gw = a.pool_scores ? a.pool_scores + (size_t)b * a.score_total : nullptr;
@@ -431,6 +434,21 @@ aasist_graph_kernel(const GraphArgsAasist a) {
     s = warp_sum(s);
     if (lane == 0) a.logits[(size_t)b * 2 + o] = s + (o == 0 ? a.outB0 : a.outB1);
   }
+  __syncthreads();   // shared buffers are reused by the next utterance
+  }
+}
+
+// grid for a per-utterance kernel: as many CTAs as utterances up to the resident capacity, then the smallest
+// grid that gives every CTA the same number of utterances (512 utterances on 444 slots: 256 CTAs x 2, not
+// 444 + a 68-CTA tail wave)
+template <typename Kernel>
+static int balanced_grid(Kernel kern, int B, size_t smem, int device) {
+  int per_sm = 1, sms = 148;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kGraphThreads, smem);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const int slots = std::max(1, per_sm * sms);
+  const int waves = (B + slots - 1) / slots;
+  return (B + waves - 1) / waves;
 }
 
 int launch_graph_aasist(aasist_handle* h, const float* e, int B, int NT, float* last_hidden,
@@ -462,7 +480,8 @@ int launch_graph_aasist(aasist_handle* h, const float* e, int B, int NT, float* 
                                    (int)smem));
   {
     LaunchSpan span(h, "aasist_graph", st);
-    aasist_graph_kernel<<<B, kGraphThreads, smem, st>>>(a);
+    a.B = B;
+    aasist_graph_kernel<<<balanced_grid(aasist_graph_kernel, B, smem, h->device), kGraphThreads, smem, st>>>(a);
   }
   AASIST_CUDA(cudaGetLastError());
   return 0;
