@@ -54,6 +54,10 @@ SIGNATURES = {
                                       C.c_void_p, C.c_void_p]),
     "aasist_pad_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.c_int32,
                                    C.c_int32, C.c_void_p, C.c_void_p]),
+    "aasist_det_workspace_bytes": (C.c_int64, [C.c_int64]),
+    "aasist_det_metrics": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_double, C.c_double,
+                                     C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_int64, C.c_void_p]),
     "aasist_get_filterbank": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "aasist_frontend": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                   C.c_int64, C.c_void_p]),

@@ -129,6 +129,26 @@ int aasist_forward_host(aasist_handle* h, const float* x_host, int32_t B, int32_
 int aasist_pad_batch(aasist_handle* h, const float* samples_dev, const int64_t* offsets_host,
                      const int32_t* lengths_host, int32_t B, int32_t max_len, float* out_dev, void* stream);
 
+/* ---- detection metrics (the step after the path) ---------------------------------------------- */
+/* Replaces compute_det_curve / compute_eer (evaluation.py:120-154) and the t-DCF curve of compute_tDCF
+ * (evaluation.py:266-282) for scores that are already in device memory (float64, as numpy holds them):
+ * stable ascending sort of the concatenation [targets, nontargets], running target count,
+ *   frr[i] = cum_i / n_target,  far[i] = (n_nontarget - (i - cum_i)) / n_nontarget,  frr[0] = 0, far[0] = 1,
+ *   thr[0] = min score - 0.001, thr[i] = i-th smallest score,
+ *   tdcf[i] = (c1 * frr[i] + c2 * far[i]) / min(c1, c2)     (skipped when c1 < 0 and c2 < 0),
+ * all in IEEE float64 with the reference's operation order: every value is bit-identical to numpy's.
+ * results_host[8] = { EER = (frr[k] + far[k]) / 2 at k = first argmin |frr - far|, thr[k], k,
+ *                     min t-DCF, its threshold, its index (first argmin), number of distinct scores,
+ *                     flags (bit 0: a score is NaN or infinite) }.
+ * The four curve outputs are optional device arrays of n_target + n_nontarget + 1 doubles (NULL to skip).
+ * Stateless (no handle); synchronises `stream` before returning.  c1/c2 are the caller's
+ * C1 = Ptar*(Cmiss_cm - Cmiss_asv*Pmiss_asv) - Pnon*Cfa_asv*Pfa_asv, C2 = Cfa_cm*Pspoof*(1 - Pmiss_spoof_asv). */
+int64_t aasist_det_workspace_bytes(int64_t n_total);
+int aasist_det_metrics(const double* target_dev, int64_t n_target, const double* nontarget_dev,
+                       int64_t n_nontarget, double c1, double c2, double* results_host,
+                       double* frr_dev, double* far_dev, double* thr_dev, double* tdcf_dev,
+                       void* workspace_dev, int64_t workspace_bytes, void* stream);
+
 /* ---- per-stage entry points (parity tests; same kernels as aasist_forward) -------------- */
 /* Device copy of the sinc filter bank, (n_filters, taps) fp32, into `bank_dev`. */
 int aasist_get_filterbank(aasist_handle* h, float* bank_dev, int32_t* n_filters, int32_t* taps);
