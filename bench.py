@@ -34,13 +34,18 @@ def parse():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--model", default="AASIST", choices=["AASIST", "AASIST-L", "RawGAT-ST"])
     ap.add_argument("--batch", type=int, default=512)
+    ap.add_argument("--samples", type=int, default=64600,
+                    help="utterance length (SURVEY 8(d) C5 length sweep; the headline metric is quoted at 64600)")
     ap.add_argument("--precision", default=None, help="fp32 | f16x3 (default: package default)")
     ap.add_argument("--workload", default="batch", choices=["batch", "evalset"],
                     help="batch: BASELINE configs[1] (default, the contract line); evalset: configs[2], one pass over "
                          "71,237 synthetic utterances sharded across the ranks with one score all-gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    args = ap.parse_args()
+    global L_SAMPLES
+    L_SAMPLES = args.samples
+    return args
 
 
 # ------------------------------------------------------------------------------------------------
@@ -344,6 +349,7 @@ def run_native(args):
                             "aasist_b200/workmodel.py) / mean CUDA-event launch time; the f16x3 path executes 3 "
                             "tcgen05 MMAs per reference MAC, so tensor-pipe work is 3x this figure; traffic = ncu "
                             "dram bytes per launch (profiles/ncu_traffic.json)"}
+    from aasist_b200 import workmodel
     line = {
         "metric": "AASIST utterances/sec (4 s, 64600 samples)", "value": value, "unit": "utt/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
@@ -359,7 +365,8 @@ def run_native(args):
         "roofline": roofline,
         "kernels": [{"kernel": r["kernel"], "launches": r["launches"], "ms_per_step": r["ms"] / args.steps,
                      "share": r["ms"] / total_kernel_ms} for r in prof],
-        "algorithmic_tflops": value * FLOPS_PER_UTT[name] / 1e12,
+        "algorithmic_tflops": value * (FLOPS_PER_UTT[name] if L_SAMPLES == 64600 else
+                                       2.0 * sum(workmodel.stage_macs(name, L_SAMPLES).values())) / 1e12,
     }
     if not args.no_cpu_baseline and world >= 1:
         n_cpu = 8
