@@ -707,24 +707,29 @@ int aasist_forward_host(aasist_handle* h, const float* x_host, int32_t B, int32_
     memcpy(h->pin_x, x_host, xb);
     src = h->pin_x;
   }
-  // chunked pipeline: the H2D copy of chunk c+1 (copy stream) overlaps the forward of chunk c
   if (!h->copy_stream) {
     AASIST_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) AASIST_CUDA(cudaEventCreateWithFlags(&h->copy_done[i], cudaEventDisableTiming));
     AASIST_CUDA(cudaEventCreateWithFlags(&h->start_ev, cudaEventDisableTiming));
   }
-  const int chunk = 128;
+  // pipeline: a small first piece (its copy is the only one exposed), then the rest of the batch in ONE forward
+  // whose copy hides behind the first piece's compute -- large encoder passes are ~3 % more efficient than 128s
+  const int first = std::min(B, 128);
   float* d_lh = dout;
   float* d_lg = dout + (size_t)B * hd;
   AASIST_CUDA(cudaEventRecord(h->start_ev, st));                 // staging buffers are free once prior work is done
   AASIST_CUDA(cudaStreamWaitEvent(h->copy_stream, h->start_ev, 0));
-  int nchunks = (B + chunk - 1) / chunk;
-  for (int c = 0; c < nchunks; ++c) {
-    const int b0 = c * chunk, nb = std::min(chunk, B - b0);
-    AASIST_CUDA(cudaMemcpyAsync(dx + (size_t)b0 * L, src + (size_t)b0 * L, sizeof(float) * (size_t)nb * L,
-                                cudaMemcpyHostToDevice, h->copy_stream));
-    AASIST_CUDA(cudaEventRecord(h->copy_done[c & 1], h->copy_stream));
-    AASIST_CUDA(cudaStreamWaitEvent(st, h->copy_done[c & 1], 0));
+  const int piece_b0[2] = {0, first}, piece_nb[2] = {first, B - first};
+  for (int c = 0; c < 2; ++c) {                                  // both copies are queued before any compute
+    if (piece_nb[c] <= 0) continue;
+    AASIST_CUDA(cudaMemcpyAsync(dx + (size_t)piece_b0[c] * L, src + (size_t)piece_b0[c] * L,
+                                sizeof(float) * (size_t)piece_nb[c] * L, cudaMemcpyHostToDevice, h->copy_stream));
+    AASIST_CUDA(cudaEventRecord(h->copy_done[c], h->copy_stream));
+  }
+  for (int c = 0; c < 2; ++c) {
+    if (piece_nb[c] <= 0) continue;
+    const int b0 = piece_b0[c], nb = piece_nb[c];
+    AASIST_CUDA(cudaStreamWaitEvent(st, h->copy_done[c], 0));
     if ((rc = aasist_forward(h, dx + (size_t)b0 * L, nb, L, d_lh + (size_t)b0 * hd, d_lg + (size_t)b0 * 2, nullptr,
                              nullptr, dws, ws_bytes, stream)))
       return rc;

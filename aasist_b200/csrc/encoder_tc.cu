@@ -36,10 +36,15 @@ constexpr int kBoxRows = kTileJ + 2;        // rows j0-1 .. j0+128
 constexpr int kSlabBytes = 17 * 1024;       // 130 rows x 128 B, rounded up to the 1024-B swizzle atom
 // epilogue warps: every warp owns 16 accumulator columns of one TMEM lane quadrant (COP/16 warps per quadrant)
 constexpr int kMaxSlots = 8;
-static int tc_chunk() {                     // utterances per encoder pass (bounds scratch: ~60 MB each)
+// utterances per encoder pass: as many as the batch has, up to 512 and up to 40 GB of scratch (≈ 59 MB per
+// 4 s utterance) -- larger passes mean fewer launches and shorter tails (512 vs 256: +3 % at batch 512);
+// AASIST_TC_CHUNK overrides
+static int tc_chunk(size_t bytes_per_utt) {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("AASIST_TC_CHUNK"); v = e ? std::max(1, atoi(e)) : 256; }
-  return v;
+  if (v < 0) { const char* e = getenv("AASIST_TC_CHUNK"); v = e ? std::max(1, atoi(e)) : 0; }
+  if (v > 0) return v;
+  const size_t budget = (size_t)40 << 30;
+  return (int)std::max<size_t>(1, std::min<size_t>(512, budget / std::max<size_t>(bytes_per_utt, 1)));
 }
 
 enum { TC_CONV1 = 0, TC_CONV2_ID = 1, TC_CONV2_DS = 2 };
@@ -783,7 +788,7 @@ static inline size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 size_t tc_workspace_bytes(const aasist_handle* h, int B, int L) {
   TcPlan pl;
   make_tc_plan(h, L, pl);
-  size_t nb = std::min(B, tc_chunk());
+  size_t nb = std::min(B, tc_chunk(pl.z + pl.mid + 2 * pl.act));
   return al256(pl.z * nb) + al256(pl.mid * nb) + 2 * al256(pl.act * nb) + 1024;
 }
 
@@ -903,7 +908,7 @@ static int run_block_tc(aasist_handle* h, int enc, int index, const __half* in_p
 int tc_encode(aasist_handle* h, const float* x, int B, int L, float** enc_out, void* ws, cudaStream_t st) {
   TcPlan pl;
   make_tc_plan(h, L, pl);
-  const int nbmax = std::min(B, tc_chunk());
+  const int nbmax = std::min(B, tc_chunk(pl.z + pl.mid + 2 * pl.act));
   char* w = (char*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
   float* z = (float*)w;
   w += al256(pl.z * nbmax);
