@@ -52,7 +52,6 @@ enum { TC_CONV1 = 0, TC_CONV2_ID = 1, TC_CONV2_DS = 2 };
 struct ConvTcParams {
   int B, H_out, J, n_jt, W_in, Co, Wo, Jn;
   int n_slots;
-  int dbg;                 // timing experiments only (AASIST_TC_DEBUG): 1 = hi*hi product only, 2 = no epilogue math
   const float* bias;       // [COP]
   __half* out;             // CONV1: [B][24][3][J][2*COP]; CONV2: [B][23][3][Jn][2*COP]
   float* out_f32;          // last block: (B,Co,23,Wo) fp32 NCHW (then `out` is unused)
@@ -86,12 +85,13 @@ __device__ __forceinline__ float ex2_approx(float x) {   // one MUFU.EX2, flush-
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float selu_fast(float v) {
-  // scale*max(v,0) + min(0, scale*alpha*(2^(v*log2e) - 1)); the negative branch goes through
-  // MUFU.EX2: |abs error| <= ~2.5e-7, the same order as the fp16-pair representation error
-  const float e = ex2_approx(v * 1.4426950408889634f);
+__device__ __forceinline__ float selu_scaled(float y) {
+  // SELU of v given y = v*log2(e) (conv1 weights and bias are pre-scaled by log2(e) when they are packed):
+  // scale*max(v,0) + min(0, scale*alpha*(2^y - 1)); the negative branch goes through MUFU.EX2:
+  // |abs error| <= ~2.5e-7, the same order as the fp16-pair representation error
+  const float e = ex2_approx(y);
   const float n = fminf(fmaf(e, kSeluScale * kSeluAlpha, -(kSeluScale * kSeluAlpha)), 0.f);
-  return fmaf(fmaxf(v, 0.f), kSeluScale, n);
+  return fmaf(fmaxf(y, 0.f), kSeluScale * 0.6931471805599453f, n);
 }
 
 // (a,b) fp32 -> packed hi half2 and lo half2 (a ~= hi+lo to 2^-22), saturating at the fp16 range.
@@ -204,10 +204,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull = bars + 2 * kMaxSlots;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* s_bias = reinterpret_cast<float*>(tempty + 4);          // [COP] (registers are scarce in the epilogue)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_strips = p.B * p.n_jt;
   const bool two_pass = p.n_slots >= 6;
+  if (threadIdx.x < COP) s_bias[threadIdx.x] = __ldg(p.bias + threadIdx.x);
 
   // weights: global image -> shared (generic proxy), then make visible to the async proxy
   for (int i = threadIdx.x; i < p.wimg_bytes / 16; i += NTHREADS)
@@ -293,10 +295,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int kc = 0; kc < KC; ++kc) {               // +32 B per K chunk == +2 in the descriptor
         if (kc < nkc) {
           umma_f16(d_tmem, a_hi + 2 * kc, w_hi + 2 * kc, idesc, (kc > 0 || !fresh) ? 1u : 0u);
-          if (!(p.dbg & 1)) {
-            umma_f16(d_tmem, a_lo + 2 * kc, w_hi + 2 * kc, idesc, 1);
-            umma_f16(d_tmem, a_hi + 2 * kc, w_lo + 2 * kc, idesc, 1);
-          }
+          umma_f16(d_tmem, a_lo + 2 * kc, w_hi + 2 * kc, idesc, 1);
+          umma_f16(d_tmem, a_hi + 2 * kc, w_lo + 2 * kc, idesc, 1);
         }
       }
     };
@@ -419,11 +419,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int part = (warp - 2) >> 2;                 // which 16-column slice of the accumulators
     const int r = quad * 32 + lane;
     const int col0 = part * 16;
-    float bias[NCH][16];
-#pragma unroll
-    for (int c = 0; c < NCH; ++c)
-#pragma unroll
-      for (int i = 0; i < 16; ++i) bias[c][i] = __ldg(p.bias + col0 + c * 16 + i);
+    const float* bias0 = s_bias + col0;
     int tcount = 0;
     for (int t = blockIdx.x; t < n_strips; t += gridDim.x) {
       const int jt = t % p.n_jt, b = t / p.n_jt;
@@ -448,16 +444,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[buf]);
-          if (p.dbg & 2) continue;
+          // warp-uniform: all three phases of every row of this warp lie inside [0, W_in)
+          const bool valid_all = 3 * (jt * kTileJ + quad * 32 + 31) + 2 < p.W_in;
 #pragma unroll
           for (int s = 0; s < 3; ++s) {
-            const bool valid = 3 * j + s < p.W_in;
+            const bool valid = valid_all || 3 * j + s < p.W_in;
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
               float v[16];
 #pragma unroll
-              for (int i = 0; i < 16; ++i)
-                v[i] = valid ? selu_fast(__uint_as_float(acc[s][c][i]) + bias[c][i]) : 0.f;
+              for (int q = 0; q < 4; ++q) {
+                const float4 bb = *reinterpret_cast<const float4*>(bias0 + c * 16 + 4 * q);
+                v[4 * q] = selu_scaled(__uint_as_float(acc[s][c][4 * q]) + bb.x);
+                v[4 * q + 1] = selu_scaled(__uint_as_float(acc[s][c][4 * q + 1]) + bb.y);
+                v[4 * q + 2] = selu_scaled(__uint_as_float(acc[s][c][4 * q + 2]) + bb.z);
+                v[4 * q + 3] = selu_scaled(__uint_as_float(acc[s][c][4 * q + 3]) + bb.w);
+              }
+              if (!valid) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = 0.f;
+              }
               if (j < p.J) {
                 __half* o = p.out + ((((size_t)b * 24 + h) * 3 + s) * p.J + j) * (2 * COP) + col0 + c * 16;
                 store_pair16<true>(o, o + COP, v);
@@ -480,7 +486,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[buf]);
-          if (p.dbg & 2) continue;
 #pragma unroll
           for (int c = 0; c < NCH; ++c) {
             float m[16];
@@ -502,7 +507,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int i = 0; i < 16; ++i) m[i] = s == 0 ? v[i] : fmaxf(m[i], v[i]);
             }
 #pragma unroll
-            for (int i = 0; i < 16; ++i) m[i] = valid ? m[i] + bias[c][i] : 0.f;
+            for (int i = 0; i < 16; ++i) m[i] = valid ? m[i] + bias0[c * 16 + i] : 0.f;
             if (p.out_f32) {
               if (valid)
 #pragma unroll
@@ -675,9 +680,9 @@ static int pack_block_tc(aasist_handle* h, const std::string& pfx, int index, Bl
   } else {
     const int tap_bytes = (blk.cpi / 32) * blk.cop * 128;
     std::vector<uint8_t> img((size_t)6 * tap_bytes, 0);
-    // 32 -> 32 identity blocks run in block_fused_tc.cu, whose transformers evaluate SELU from
-    // y = v * log2(e): conv1 (and its bias, the accumulators' start value there) is pre-scaled
-    const double pre = is_fused_block(blk) ? 1.4426950408889634 : 1.0;
+    // conv1's SELU is evaluated from y = v * log2(e) everywhere on this path (conv_tc_kernel's CONV1 epilogue,
+    // the transformers of block_fused_tc.cu): conv1 and its bias are pre-scaled
+    const double pre = 1.4426950408889634;
     for (int o = 0; o < co; ++o) {
       bias1[o] = (float)((double)bias1[o] * pre);
       for (int i = 0; i < ci; ++i)
@@ -800,21 +805,19 @@ template <int CPI, int COP, int MODE>
 static int launch_conv(aasist_handle* h, const char* name, const CUtensorMap& tmA, const CUtensorMap& tmS,
                        ConvTcParams p, cudaStream_t st) {
   constexpr int SLOT = (CPI / 32) * kSlabBytes;
-  const int budget = 227 * 1024 - 1024 /*align*/ - p.wimg_bytes - 256 /*barriers*/;
+  const int budget = 227 * 1024 - 1024 /*align*/ - p.wimg_bytes - 512 /*barriers, bias*/;
   int n_slots = std::min(kMaxSlots, budget / SLOT);
   if (n_slots < 2) {
     set_error("conv_tc: not enough shared memory for the input ring (weights %d bytes)", p.wimg_bytes);
     return AASIST_E_INVALID;
   }
   {
-    static int dbg = -1, slots_override = -1;
-    if (dbg < 0) { const char* e = getenv("AASIST_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+    static int slots_override = -1;
     if (slots_override < 0) { const char* e = getenv("AASIST_TC_SLOTS"); slots_override = e ? atoi(e) : 0; }
-    p.dbg = dbg;
     if (slots_override >= 2 && slots_override <= n_slots) n_slots = slots_override;
   }
   p.n_slots = n_slots;
-  size_t smem = 1024 + (size_t)p.wimg_bytes + (size_t)n_slots * SLOT + 256;
+  size_t smem = 1024 + (size_t)p.wimg_bytes + (size_t)n_slots * SLOT + 512;
   auto kern = conv_tc_kernel<CPI, COP, MODE>;
   AASIST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int n_strips = p.B * p.n_jt;
