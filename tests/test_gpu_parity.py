@@ -220,3 +220,31 @@ def test_parameter_updates_are_picked_up():
     sd = load_sd("AASIST-L")
     m.load_state_dict(sd)                                # reload -> back to the original logits
     assert torch.equal(m(x)[1], out0)
+
+
+def test_custom_config_with_widths_that_are_not_multiples_of_8():
+    """gat_dims [20, 12] / 20 encoder channels: exercises the graph kernel's staged attention-projection path
+    (the shipped configs all take the unstaged one) and channel padding in the encoder, fp32 and f16x3."""
+    import aasist_b200
+    g = _g()
+    cfg = {"architecture": "AASIST", "nb_samp": 64600, "first_conv": 128,
+           "filts": [70, [1, 32], [32, 32], [32, 20], [20, 20]], "gat_dims": [20, 12],
+           "pool_ratios": [0.5, 0.7, 0.5, 0.5], "temperatures": [2.0, 2.0, 100.0, 100.0]}
+    torch.manual_seed(7)
+    ref_model = aasist_b200.Model(cfg, precision="fp32")
+    sd = ref_model.state_dict()
+    for k, v in sd.items():                                  # non-trivial BN statistics and biases
+        if k.endswith("running_var"):
+            v.copy_(torch.rand_like(v) * 1.5 + 0.25)
+        elif k.endswith("running_mean") or k.endswith(".bias"):
+            v.copy_(torch.randn_like(v) * 0.1)
+    x = O.speech_like(3, 20000, 11)
+    torch.set_num_threads(8)
+    _, ref = O.forward("AASIST", sd, cfg, x)
+    for precision, tol in (("fp32", LOGIT_TOL), ("f16x3", 2e-4)):
+        m = aasist_b200.Model(cfg, precision=precision)
+        m.load_state_dict(sd, strict=True)
+        m = m.to(g.DEV).eval()
+        _, out = m(x.to(g.DEV))
+        err = (out.cpu() - ref).abs().max().item()
+        assert err <= tol * max(1.0, ref.abs().max().item()), (precision, err)
