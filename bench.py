@@ -342,13 +342,15 @@ def run_native(args):
             pass
         roofline = {"bound": "tensor", "kernel": top["kernel"], "achieved": ach, "peak": peak_tf,
                     "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
+                    "executed_tflops": 3.0 * ach if precision == "f16x3" else ach,
+                    "executed_frac": (3.0 * ach if precision == "f16x3" else ach) / peak_tf,
                     "peak_source": peak_src, "share_of_step": top["ms"] / total_kernel_ms,
                     "flops_per_launch": flops_step / n_launch, "launches_per_step": n_launch,
                     "avg_launch_ms": avg_launch_ms,
                     "note": "achieved = ALGORITHMIC FLOPs per launch (2xMAC of the reference fp32 ops, "
                             "aasist_b200/workmodel.py) / mean CUDA-event launch time; the f16x3 path executes 3 "
-                            "tcgen05 MMAs per reference MAC, so tensor-pipe work is 3x this figure; traffic = ncu "
-                            "dram bytes per launch (profiles/ncu_traffic.json)"}
+                            "tcgen05 MMAs per reference MAC, so tensor-pipe work is 3x this figure (executed_tflops / "
+                            "executed_frac); traffic = ncu dram bytes per launch (profiles/ncu_traffic.json)"}
     from aasist_b200 import workmodel
     line = {
         "metric": "AASIST utterances/sec (4 s, 64600 samples)", "value": value, "unit": "utt/s",

@@ -105,3 +105,20 @@ def test_tc_larger_batch_crosses_chunk_boundary():
     out = m(big)[1]
     ref = m(x)[1]
     assert torch.equal(out.view(50, 3, 2), ref.unsqueeze(0).expand(50, 3, 2))
+
+
+@pytest.mark.parametrize("B,L", [(1, 64600), (5, 2400), (3, 16001), (7, 30011), (130, 9000), (2, 131072)])
+def test_tc_path_agrees_with_fp32_path_on_odd_shapes(B, L):
+    """Strip/tile edge handling (partial strips, J not a multiple of 126/128, tiny widths in the last blocks,
+    batch sizes around the CTA count): the tensor-core path against the CUDA-core fp32 path, which the other
+    tests pin to the oracle."""
+    g = _g()
+    x = O.speech_like(B, L, 100 + B).to(g.DEV)
+    h32, o32 = g.native_model("AASIST", "fp32")(x)
+    h16, o16 = g.native_model("AASIST", "f16x3")(x)
+    torch.cuda.synchronize()
+    assert torch.isfinite(o16).all()
+    err = (o16 - o32).abs().max().item()
+    herr = (h16 - h32).abs().max().item()
+    print(json.dumps({"B": B, "L": L, "logit_err": err, "hidden_err": herr}))
+    assert err <= TC_LOGIT_TOL and herr <= TC_LOGIT_TOL, (err, herr)
