@@ -52,6 +52,9 @@ enum { TC_CONV1 = 0, TC_CONV2_ID = 1, TC_CONV2_DS = 2 };
 struct ConvTcParams {
   int B, H_out, J, n_jt, W_in, Co, Wo, Jn;
   int n_slots;
+  // short rows (the last encoder blocks): `segs` utterances share one 128-row tile, each in a `seg_rows`-row
+  // segment (positions -1 .. seg_rows-2, multiple of 8 rows so the swizzle atoms line up); segs == 1: one strip
+  int segs, seg_rows, n_strips;
   const float* bias;       // [COP]
   __half* out;             // CONV1: [B][24][3][J][2*COP]; CONV2: [B][23][3][Jn][2*COP]
   float* out_f32;          // last block: (B,Co,23,Wo) fp32 NCHW (then `out` is unused)
@@ -207,7 +210,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   float* s_bias = reinterpret_cast<float*>(tempty + 4);          // [COP] (registers are scarce in the epilogue)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_strips = p.B * p.n_jt;
+  const int n_strips = p.n_strips;
   const bool two_pass = p.n_slots >= 6;
   if (threadIdx.x < COP) s_bias[threadIdx.x] = __ldg(p.bias + threadIdx.x);
 
@@ -239,24 +242,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int slot = 0;
       uint32_t phase = 0;
+      const bool packed = p.segs > 1;
+      const uint32_t box_bytes = (uint32_t)(packed ? p.seg_rows : kBoxRows) * 128u;
       for (int t = blockIdx.x; t < n_strips; t += gridDim.x) {
-        const int jt = t % p.n_jt, b = t / p.n_jt;
+        const int jt = packed ? 0 : t % p.n_jt, b = packed ? t * p.segs : t / p.n_jt;
+        const int nseg = packed ? min(p.segs, p.B - b) : 1;        // utterances in this tile
         const int j0 = jt * kTileJ - 1;
         for (int r = 0; r < R_IN; ++r) {
           for (int phi = 0; phi < 3; ++phi) {
             mbar_wait(&empty[slot], phase ^ 1);
             uint8_t* dst = s_ring + (size_t)slot * SLOT_BYTES;
-            mbar_arrive_expect_tx(&full[slot], SLABS * kBoxRows * 128);
+            mbar_arrive_expect_tx(&full[slot], SLABS * nseg * box_bytes);
+            for (int g = 0; g < nseg; ++g)
 #pragma unroll
-            for (int sl = 0; sl < SLABS; ++sl)
-              tma_load_5d(dst + sl * kSlabBytes, &tmA, &full[slot], sl * 64, j0, phi, r, b);
+              for (int sl = 0; sl < SLABS; ++sl)
+                tma_load_5d(dst + sl * kSlabBytes + (size_t)g * box_bytes, &tmA, &full[slot], sl * 64, j0, phi, r, b + g);
             if (++slot == p.n_slots) { slot = 0; phase ^= 1; }
           }
           if (HAS_SIDE && r < 23) {   // conv_downsample input: block input row h = r (output row r)
             for (int phi = 0; phi < 3; ++phi) {
               mbar_wait(&empty[slot], phase ^ 1);
-              mbar_arrive_expect_tx(&full[slot], kBoxRows * 128);
-              tma_load_5d(s_ring + (size_t)slot * SLOT_BYTES, &tmS, &full[slot], 0, j0, phi, r, b);
+              mbar_arrive_expect_tx(&full[slot], nseg * box_bytes);
+              for (int g = 0; g < nseg; ++g)
+                tma_load_5d(s_ring + (size_t)slot * SLOT_BYTES + (size_t)g * box_bytes, &tmS, &full[slot], 0, j0, phi, r,
+                            b + g);
               if (++slot == p.n_slots) { slot = 0; phase ^= 1; }
             }
           }
@@ -422,8 +431,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const float* bias0 = s_bias + col0;
     int tcount = 0;
     for (int t = blockIdx.x; t < n_strips; t += gridDim.x) {
-      const int jt = t % p.n_jt, b = t / p.n_jt;
-      const int j = jt * kTileJ + r;
+      int jt = t % p.n_jt, b = t / p.n_jt, j = jt * kTileJ + r;
+      if (p.segs > 1) {                     // packed tile: accumulator row r = (utterance t*segs + g, column r - g*seg_rows)
+        const int g = r / p.seg_rows;
+        jt = 0;
+        b = t * p.segs + g;
+        j = r - g * p.seg_rows;
+        if (g >= p.segs || b >= p.B) { b = p.B - 1; j = 1 << 28; }   // no utterance here: every guard below fails
+      }
       for (int h = 0; h < p.H_out; ++h, ++tcount) {
         const int buf = tcount & 1;
         const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 3 * COP + col0);
@@ -445,7 +460,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[buf]);
           // warp-uniform: all three phases of every row of this warp lie inside [0, W_in)
-          const bool valid_all = 3 * (jt * kTileJ + quad * 32 + 31) + 2 < p.W_in;
+          const bool valid_all = p.segs == 1 && 3 * (jt * kTileJ + quad * 32 + 31) + 2 < p.W_in;
 #pragma unroll
           for (int s = 0; s < 3; ++s) {
             const bool valid = valid_all || 3 * j + s < p.W_in;
@@ -574,7 +589,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_act_tmap(aasist_handle* h, CUtensorMap* m, const void* base, int Cp, int J, int H, int B) {
+static int make_act_tmap(aasist_handle* h, CUtensorMap* m, const void* base, int Cp, int J, int H, int B,
+                         int box_rows = kBoxRows) {
   EncodeTiledFn fn = (EncodeTiledFn)h->tc->encode_fn;
   cuuint64_t dims[5] = {(cuuint64_t)(2 * Cp), (cuuint64_t)J, 3, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[4];
@@ -582,7 +598,7 @@ static int make_act_tmap(aasist_handle* h, CUtensorMap* m, const void* base, int
   strides[1] = strides[0] * J;
   strides[2] = strides[1] * 3;
   strides[3] = strides[2] * H;
-  cuuint32_t box[5] = {64, (cuuint32_t)kBoxRows, 1, 1, 1};
+  cuuint32_t box[5] = {64, (cuuint32_t)box_rows, 1, 1, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -820,7 +836,9 @@ static int launch_conv(aasist_handle* h, const char* name, const CUtensorMap& tm
   size_t smem = 1024 + (size_t)p.wimg_bytes + (size_t)n_slots * SLOT + 512;
   auto kern = conv_tc_kernel<CPI, COP, MODE>;
   AASIST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int n_strips = p.B * p.n_jt;
+  if (p.segs < 1) { p.segs = 1; p.seg_rows = kTileJ; }
+  const int n_strips = p.segs > 1 ? (p.B + p.segs - 1) / p.segs : p.B * p.n_jt;
+  p.n_strips = n_strips;
   const int grid = std::min(n_strips, h->tc->sm_count);
   static int want_stats = -1;
   if (want_stats < 0) { const char* e = getenv("AASIST_TC_STATS"); want_stats = e ? atoi(e) : 0; }
@@ -866,11 +884,25 @@ static int run_block_tc(aasist_handle* h, int enc, int index, const __half* in_p
     return AASIST_E_INVALID;
   }
   int rc;
-  CUtensorMap tmIn, tmMid;
+  // tile plans: rows a strip must cover (conv2 also writes the zero rows up to 3*Jn of the next block's layout);
+  // when they fit a 64-row segment, several utterances share one 128-row tile
+  const int rows1 = J, rows2 = std::max(J, std::min(3 * Jn, Wo + 2));
+  auto seg_plan = [](int rows, int& seg_rows, int& segs) {
+    seg_rows = ((rows + 2 + 7) / 8) * 8;
+    segs = seg_rows <= 64 ? kTileJ / seg_rows : 1;
+    if (segs == 1) seg_rows = kTileJ;
+  };
+  int sr1, sg1, sr2, sg2;
+  seg_plan(rows1, sr1, sg1);
+  seg_plan(rows2, sr2, sg2);
+  CUtensorMap tmIn, tmMid, tmIn2;
   memset(&tmIn, 0, sizeof(tmIn));
   memset(&tmMid, 0, sizeof(tmMid));
-  if (index > 0 && (rc = make_act_tmap(h, &tmMid, mid, blk.cop, J, 24, nb))) return rc;
-  if (index > 0 && (rc = make_act_tmap(h, &tmIn, in_pairs, blk.cpi, J, 23, nb))) return rc;
+  memset(&tmIn2, 0, sizeof(tmIn2));
+  const bool fused_path = index == 0 || is_fused_block(blk);
+  if (index > 0 && (rc = make_act_tmap(h, &tmMid, mid, blk.cop, J, 24, nb, (!fused_path && sg2 > 1) ? sr2 : kBoxRows))) return rc;
+  if (index > 0 && (rc = make_act_tmap(h, &tmIn, in_pairs, blk.cpi, J, 23, nb, (!fused_path && sg1 > 1) ? sr1 : kBoxRows))) return rc;
+  if (index > 0 && (rc = make_act_tmap(h, &tmIn2, in_pairs, blk.cpi, J, 23, nb, (!fused_path && sg2 > 1) ? sr2 : kBoxRows))) return rc;
   // ---- block 0 and 32->32 identity blocks: the whole block is one kernel, intermediate kept on chip ----
   if (index == 0)
     return launch_block0_tc(h, h->tc->sm_count, blk.b0_img, blk.c1.bias, blk.c2.bias, z, nb, W, out_pairs, st);
@@ -883,7 +915,8 @@ static int run_block_tc(aasist_handle* h, int enc, int index, const __half* in_p
   {
     ConvTcParams p;
     memset(&p, 0, sizeof(p));
-    p.B = nb; p.H_out = 24; p.J = J; p.n_jt = (J + kTileJ - 1) / kTileJ; p.W_in = W; p.Co = blk.co;
+    p.B = nb; p.H_out = 24; p.J = J; p.n_jt = (rows1 + kTileJ - 1) / kTileJ; p.W_in = W; p.Co = blk.co;
+    p.segs = sg1; p.seg_rows = sr1;
     p.bias = blk.c1.bias; p.out = mid; p.wimg = blk.c1.wimg; p.wimg_bytes = blk.c1.wimg_bytes;
     if (blk.cpi == 32 && blk.cop == 32) rc = launch_conv<32, 32, TC_CONV1>(h, kConvNames[0][index], tmIn, tmIn, p, st);   // 32 -> 24 (AASIST-L)
     else if (blk.cpi == 32 && blk.cop == 64) rc = launch_conv<32, 64, TC_CONV1>(h, kConvNames[0][index], tmIn, tmIn, p, st);
@@ -896,14 +929,15 @@ static int run_block_tc(aasist_handle* h, int enc, int index, const __half* in_p
   ConvTcParams p;
   memset(&p, 0, sizeof(p));
   p.B = nb; p.H_out = 23; p.J = J; p.W_in = W; p.Co = blk.co; p.Wo = Wo; p.Jn = Jn;
-  p.n_jt = (std::max(J, std::min(3 * Jn, Wo + 2)) + kTileJ - 1) / kTileJ;
+  p.n_jt = (rows2 + kTileJ - 1) / kTileJ;
+  p.segs = sg2; p.seg_rows = sr2;
   p.bias = blk.c2.bias; p.out = out_pairs; p.out_f32 = out_f32; p.wimg = blk.c2.wimg; p.wimg_bytes = blk.c2.wimg_bytes;
   if (!blk.downsample) {
     p.idn = in_pairs;   // 64 -> 64 identity block (the 32 -> 32 ones took the fused path above)
     rc = launch_conv<64, 64, TC_CONV2_ID>(h, kConvNames[1][index], tmMid, tmMid, p, st);
   } else {
-    if (blk.cop == 32) rc = launch_conv<32, 32, TC_CONV2_DS>(h, kConvNames[1][index], tmMid, tmIn, p, st);
-    else rc = launch_conv<64, 64, TC_CONV2_DS>(h, kConvNames[1][index], tmMid, tmIn, p, st);
+    if (blk.cop == 32) rc = launch_conv<32, 32, TC_CONV2_DS>(h, kConvNames[1][index], tmMid, tmIn2, p, st);
+    else rc = launch_conv<64, 64, TC_CONV2_DS>(h, kConvNames[1][index], tmMid, tmIn2, p, st);
   }
   return rc;
 }
