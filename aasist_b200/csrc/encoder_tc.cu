@@ -50,11 +50,13 @@ static int tc_chunk(size_t bytes_per_utt) {
 enum { TC_CONV1 = 0, TC_CONV2_ID = 1, TC_CONV2_DS = 2 };
 
 struct ConvTcParams {
-  int B, H_out, J, n_jt, W_in, Co, Wo, Jn;
+  int B, H_out, J, W_in, Co, Wo, Jn;
   int n_slots;
-  // short rows (the last encoder blocks): `segs` utterances share one 128-row tile, each in a `seg_rows`-row
-  // segment (positions -1 .. seg_rows-2, multiple of 8 rows so the swizzle atoms line up); segs == 1: one strip
-  int segs, seg_rows, n_strips;
+  // Work items: B * n_full regular strips (128 columns each), then n_tail packed tiles.  The last, partial strip
+  // of a row ("tail": rows - 128*n_full columns) is short in the deeper blocks; when it fits a 64-row segment,
+  // `segs` utterances' tails share one 128-row tile, each in a `seg_rows`-row segment (columns 128*n_full - 1 ..,
+  // a multiple of 8 rows so the swizzle atoms line up).  n_tail == 0: every strip is regular.
+  int n_full, segs, seg_rows, n_tail, n_strips;
   const float* bias;       // [COP]
   __half* out;             // CONV1: [B][24][3][J][2*COP]; CONV2: [B][23][3][Jn][2*COP]
   float* out_f32;          // last block: (B,Co,23,Wo) fp32 NCHW (then `out` is unused)
@@ -183,6 +185,7 @@ struct ConvCfg {
 template <int CPI, int COP, int MODE>
 __global__ void __launch_bounds__(ConvCfg<COP>::kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmS,
+               const __grid_constant__ CUtensorMap tmAt, const __grid_constant__ CUtensorMap tmSt,
                const ConvTcParams p) {
   constexpr int SLABS = CPI / 32;                    // 128-byte-wide K slabs per input tile
   constexpr int SLOT_BYTES = SLABS * kSlabBytes;
@@ -230,6 +233,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     fence_barrier_init();
     prefetch_tensormap(&tmA);
     if (HAS_SIDE) prefetch_tensormap(&tmS);
+    if (p.n_tail) {
+      prefetch_tensormap(&tmAt);
+      if (HAS_SIDE) prefetch_tensormap(&tmSt);
+    }
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_ptr);
   tc_fence_before_sync();
@@ -242,12 +249,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int slot = 0;
       uint32_t phase = 0;
-      const bool packed = p.segs > 1;
-      const uint32_t box_bytes = (uint32_t)(packed ? p.seg_rows : kBoxRows) * 128u;
+      const int n_regular = p.B * p.n_full;
       for (int t = blockIdx.x; t < n_strips; t += gridDim.x) {
-        const int jt = packed ? 0 : t % p.n_jt, b = packed ? t * p.segs : t / p.n_jt;
-        const int nseg = packed ? min(p.segs, p.B - b) : 1;        // utterances in this tile
-        const int j0 = jt * kTileJ - 1;
+        const bool tail = t >= n_regular;                          // packed tile of `segs` tails
+        const int b = tail ? (t - n_regular) * p.segs : t / p.n_full;
+        const int nseg = tail ? min(p.segs, p.B - b) : 1;          // utterances in this tile
+        const int j0 = (tail ? p.n_full : t % p.n_full) * kTileJ - 1;
+        const uint32_t box_bytes = (uint32_t)(tail ? p.seg_rows : kBoxRows) * 128u;
+        const CUtensorMap* mA = tail ? &tmAt : &tmA;
+        const CUtensorMap* mS = tail ? &tmSt : &tmS;
         for (int r = 0; r < R_IN; ++r) {
           for (int phi = 0; phi < 3; ++phi) {
             mbar_wait(&empty[slot], phase ^ 1);
@@ -256,7 +266,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int g = 0; g < nseg; ++g)
 #pragma unroll
               for (int sl = 0; sl < SLABS; ++sl)
-                tma_load_5d(dst + sl * kSlabBytes + (size_t)g * box_bytes, &tmA, &full[slot], sl * 64, j0, phi, r, b + g);
+                tma_load_5d(dst + sl * kSlabBytes + (size_t)g * box_bytes, mA, &full[slot], sl * 64, j0, phi, r, b + g);
             if (++slot == p.n_slots) { slot = 0; phase ^= 1; }
           }
           if (HAS_SIDE && r < 23) {   // conv_downsample input: block input row h = r (output row r)
@@ -264,7 +274,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               mbar_wait(&empty[slot], phase ^ 1);
               mbar_arrive_expect_tx(&full[slot], nseg * box_bytes);
               for (int g = 0; g < nseg; ++g)
-                tma_load_5d(s_ring + (size_t)slot * SLOT_BYTES + (size_t)g * box_bytes, &tmS, &full[slot], 0, j0, phi, r,
+                tma_load_5d(s_ring + (size_t)slot * SLOT_BYTES + (size_t)g * box_bytes, mS, &full[slot], 0, j0, phi, r,
                             b + g);
               if (++slot == p.n_slots) { slot = 0; phase ^= 1; }
             }
@@ -431,12 +441,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const float* bias0 = s_bias + col0;
     int tcount = 0;
     for (int t = blockIdx.x; t < n_strips; t += gridDim.x) {
-      int jt = t % p.n_jt, b = t / p.n_jt, j = jt * kTileJ + r;
-      if (p.segs > 1) {                     // packed tile: accumulator row r = (utterance t*segs + g, column r - g*seg_rows)
+      const bool tail = t >= p.B * p.n_full;
+      int jt, b, j;
+      if (!tail) {
+        jt = t % p.n_full;
+        b = t / p.n_full;
+        j = jt * kTileJ + r;
+      } else {                              // packed tile: accumulator row r = (utterance, column) of segment g
         const int g = r / p.seg_rows;
-        jt = 0;
-        b = t * p.segs + g;
-        j = r - g * p.seg_rows;
+        jt = p.n_full;
+        b = (t - p.B * p.n_full) * p.segs + g;
+        j = p.n_full * kTileJ + (r - g * p.seg_rows);
         if (g >= p.segs || b >= p.B) { b = p.B - 1; j = 1 << 28; }   // no utterance here: every guard below fails
       }
       for (int h = 0; h < p.H_out; ++h, ++tcount) {
@@ -460,7 +475,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[buf]);
           // warp-uniform: all three phases of every row of this warp lie inside [0, W_in)
-          const bool valid_all = p.segs == 1 && 3 * (jt * kTileJ + quad * 32 + 31) + 2 < p.W_in;
+          const bool valid_all = !tail && 3 * (jt * kTileJ + quad * 32 + 31) + 2 < p.W_in;
 #pragma unroll
           for (int s = 0; s < 3; ++s) {
             const bool valid = valid_all || 3 * j + s < p.W_in;
@@ -819,7 +834,7 @@ static const char* kConvNames[2][6] = {
 
 template <int CPI, int COP, int MODE>
 static int launch_conv(aasist_handle* h, const char* name, const CUtensorMap& tmA, const CUtensorMap& tmS,
-                       ConvTcParams p, cudaStream_t st) {
+                       const CUtensorMap& tmAt, const CUtensorMap& tmSt, ConvTcParams p, cudaStream_t st) {
   constexpr int SLOT = (CPI / 32) * kSlabBytes;
   const int budget = 227 * 1024 - 1024 /*align*/ - p.wimg_bytes - 512 /*barriers, bias*/;
   int n_slots = std::min(kMaxSlots, budget / SLOT);
@@ -836,8 +851,7 @@ static int launch_conv(aasist_handle* h, const char* name, const CUtensorMap& tm
   size_t smem = 1024 + (size_t)p.wimg_bytes + (size_t)n_slots * SLOT + 512;
   auto kern = conv_tc_kernel<CPI, COP, MODE>;
   AASIST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (p.segs < 1) { p.segs = 1; p.seg_rows = kTileJ; }
-  const int n_strips = p.segs > 1 ? (p.B + p.segs - 1) / p.segs : p.B * p.n_jt;
+  const int n_strips = p.B * p.n_full + p.n_tail;
   p.n_strips = n_strips;
   const int grid = std::min(n_strips, h->tc->sm_count);
   static int want_stats = -1;
@@ -852,7 +866,7 @@ static int launch_conv(aasist_handle* h, const char* name, const CUtensorMap& tm
   }
   {
     LaunchSpan span(h, name, st);
-    kern<<<grid, ConvCfg<COP>::kThreads, smem, st>>>(tmA, tmS, p);
+    kern<<<grid, ConvCfg<COP>::kThreads, smem, st>>>(tmA, tmS, tmAt, tmSt, p);
   }
   AASIST_CUDA(cudaGetLastError());
   if (want_stats) {   // debugging aid: where the MMA warp waits (cycles per output row-tile, mean over CTAs)
@@ -884,25 +898,42 @@ static int run_block_tc(aasist_handle* h, int enc, int index, const __half* in_p
     return AASIST_E_INVALID;
   }
   int rc;
-  // tile plans: rows a strip must cover (conv2 also writes the zero rows up to 3*Jn of the next block's layout);
-  // when they fit a 64-row segment, several utterances share one 128-row tile
+  // tile plans: columns a row's strips must cover (conv2 also writes the zero rows up to 3*Jn of the next block's
+  // layout); regular 128-column strips, and a packed tile for the tails when a tail fits a 64-row segment
   const int rows1 = J, rows2 = std::max(J, std::min(3 * Jn, Wo + 2));
-  auto seg_plan = [](int rows, int& seg_rows, int& segs) {
-    seg_rows = ((rows + 2 + 7) / 8) * 8;
-    segs = seg_rows <= 64 ? kTileJ / seg_rows : 1;
-    if (segs == 1) seg_rows = kTileJ;
+  struct StripPlan { int n_full, segs, seg_rows, n_tail; };
+  auto plan_strips = [nb](int rows) {
+    StripPlan sp;
+    sp.n_full = rows / kTileJ;
+    const int rem = rows - sp.n_full * kTileJ;
+    sp.segs = 1; sp.seg_rows = kTileJ; sp.n_tail = 0;
+    if (rem > 0) {
+      const int seg_rows = ((rem + 2 + 7) / 8) * 8;
+      if (seg_rows <= 64) {
+        sp.seg_rows = seg_rows;
+        sp.segs = kTileJ / seg_rows;
+        sp.n_tail = (nb + sp.segs - 1) / sp.segs;
+      } else {
+        sp.n_full += 1;                                  // the tail is a strip like the others
+      }
+    }
+    return sp;
   };
-  int sr1, sg1, sr2, sg2;
-  seg_plan(rows1, sr1, sg1);
-  seg_plan(rows2, sr2, sg2);
-  CUtensorMap tmIn, tmMid, tmIn2;
+  const StripPlan sp1 = plan_strips(rows1), sp2 = plan_strips(rows2);
+  CUtensorMap tmIn, tmMid, tmInT1, tmMidT, tmInT2;
   memset(&tmIn, 0, sizeof(tmIn));
   memset(&tmMid, 0, sizeof(tmMid));
-  memset(&tmIn2, 0, sizeof(tmIn2));
+  memset(&tmInT1, 0, sizeof(tmInT1));
+  memset(&tmMidT, 0, sizeof(tmMidT));
+  memset(&tmInT2, 0, sizeof(tmInT2));
   const bool fused_path = index == 0 || is_fused_block(blk);
-  if (index > 0 && (rc = make_act_tmap(h, &tmMid, mid, blk.cop, J, 24, nb, (!fused_path && sg2 > 1) ? sr2 : kBoxRows))) return rc;
-  if (index > 0 && (rc = make_act_tmap(h, &tmIn, in_pairs, blk.cpi, J, 23, nb, (!fused_path && sg1 > 1) ? sr1 : kBoxRows))) return rc;
-  if (index > 0 && (rc = make_act_tmap(h, &tmIn2, in_pairs, blk.cpi, J, 23, nb, (!fused_path && sg2 > 1) ? sr2 : kBoxRows))) return rc;
+  if (index > 0 && (rc = make_act_tmap(h, &tmMid, mid, blk.cop, J, 24, nb))) return rc;
+  if (index > 0 && (rc = make_act_tmap(h, &tmIn, in_pairs, blk.cpi, J, 23, nb))) return rc;
+  if (!fused_path) {
+    if ((rc = make_act_tmap(h, &tmInT1, in_pairs, blk.cpi, J, 23, nb, sp1.seg_rows))) return rc;
+    if ((rc = make_act_tmap(h, &tmMidT, mid, blk.cop, J, 24, nb, sp2.seg_rows))) return rc;
+    if ((rc = make_act_tmap(h, &tmInT2, in_pairs, blk.cpi, J, 23, nb, sp2.seg_rows))) return rc;
+  }
   // ---- block 0 and 32->32 identity blocks: the whole block is one kernel, intermediate kept on chip ----
   if (index == 0)
     return launch_block0_tc(h, h->tc->sm_count, blk.b0_img, blk.c1.bias, blk.c2.bias, z, nb, W, out_pairs, st);
@@ -915,12 +946,12 @@ static int run_block_tc(aasist_handle* h, int enc, int index, const __half* in_p
   {
     ConvTcParams p;
     memset(&p, 0, sizeof(p));
-    p.B = nb; p.H_out = 24; p.J = J; p.n_jt = (rows1 + kTileJ - 1) / kTileJ; p.W_in = W; p.Co = blk.co;
-    p.segs = sg1; p.seg_rows = sr1;
+    p.B = nb; p.H_out = 24; p.J = J; p.W_in = W; p.Co = blk.co;
+    p.n_full = sp1.n_full; p.segs = sp1.segs; p.seg_rows = sp1.seg_rows; p.n_tail = sp1.n_tail;
     p.bias = blk.c1.bias; p.out = mid; p.wimg = blk.c1.wimg; p.wimg_bytes = blk.c1.wimg_bytes;
-    if (blk.cpi == 32 && blk.cop == 32) rc = launch_conv<32, 32, TC_CONV1>(h, kConvNames[0][index], tmIn, tmIn, p, st);   // 32 -> 24 (AASIST-L)
-    else if (blk.cpi == 32 && blk.cop == 64) rc = launch_conv<32, 64, TC_CONV1>(h, kConvNames[0][index], tmIn, tmIn, p, st);
-    else if (blk.cpi == 64 && blk.cop == 64) rc = launch_conv<64, 64, TC_CONV1>(h, kConvNames[0][index], tmIn, tmIn, p, st);
+    if (blk.cpi == 32 && blk.cop == 32) rc = launch_conv<32, 32, TC_CONV1>(h, kConvNames[0][index], tmIn, tmIn, tmInT1, tmInT1, p, st);   // 32 -> 24 (AASIST-L)
+    else if (blk.cpi == 32 && blk.cop == 64) rc = launch_conv<32, 64, TC_CONV1>(h, kConvNames[0][index], tmIn, tmIn, tmInT1, tmInT1, p, st);
+    else if (blk.cpi == 64 && blk.cop == 64) rc = launch_conv<64, 64, TC_CONV1>(h, kConvNames[0][index], tmIn, tmIn, tmInT1, tmInT1, p, st);
     else { set_error("f16x3 path: unsupported conv1 shape %d->%d", blk.ci, blk.co); rc = AASIST_E_INVALID; }
     if (rc) return rc;
   }
@@ -929,15 +960,14 @@ static int run_block_tc(aasist_handle* h, int enc, int index, const __half* in_p
   ConvTcParams p;
   memset(&p, 0, sizeof(p));
   p.B = nb; p.H_out = 23; p.J = J; p.W_in = W; p.Co = blk.co; p.Wo = Wo; p.Jn = Jn;
-  p.n_jt = (rows2 + kTileJ - 1) / kTileJ;
-  p.segs = sg2; p.seg_rows = sr2;
+  p.n_full = sp2.n_full; p.segs = sp2.segs; p.seg_rows = sp2.seg_rows; p.n_tail = sp2.n_tail;
   p.bias = blk.c2.bias; p.out = out_pairs; p.out_f32 = out_f32; p.wimg = blk.c2.wimg; p.wimg_bytes = blk.c2.wimg_bytes;
   if (!blk.downsample) {
     p.idn = in_pairs;   // 64 -> 64 identity block (the 32 -> 32 ones took the fused path above)
-    rc = launch_conv<64, 64, TC_CONV2_ID>(h, kConvNames[1][index], tmMid, tmMid, p, st);
+    rc = launch_conv<64, 64, TC_CONV2_ID>(h, kConvNames[1][index], tmMid, tmMid, tmMidT, tmMidT, p, st);
   } else {
-    if (blk.cop == 32) rc = launch_conv<32, 32, TC_CONV2_DS>(h, kConvNames[1][index], tmMid, tmIn2, p, st);
-    else rc = launch_conv<64, 64, TC_CONV2_DS>(h, kConvNames[1][index], tmMid, tmIn2, p, st);
+    if (blk.cop == 32) rc = launch_conv<32, 32, TC_CONV2_DS>(h, kConvNames[1][index], tmMid, tmIn, tmMidT, tmInT2, p, st);
+    else rc = launch_conv<64, 64, TC_CONV2_DS>(h, kConvNames[1][index], tmMid, tmIn, tmMidT, tmInT2, p, st);
   }
   return rc;
 }
