@@ -28,7 +28,9 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 struct Scratch {
-  float* Wst;    // [kMaxDim][kMaxDim] staged attention projection (transposed, padded to Dop)
+  float* Wst;    // [kMaxDim][kMaxDim] staged attention projection (transposed, padded to Dop).  ALIASES the layer
+                 // output buffer and AGG (carve_layer_buffers): neither is live while the attention map is built,
+                 // and without 16 KB of its own the kernel fits four CTAs per SM instead of three
   float* vb;     // staged attB
   float* va;     // staged att weight (type 11 / plain)
   float* vb2;    // staged att weight 22
@@ -307,11 +309,11 @@ __device__ __forceinline__ float* bump(float*& p, int n) {
 
 __host__ __device__ inline int scratch_floats(int nmax) {
   int lda = nmax + 1;
-  return kMaxDim * kMaxDim + 4 * kMaxDim + ((nmax * lda + 3) & ~3) + 3 * ((nmax + 3) & ~3) + kMaxDim;
+  return 4 * kMaxDim + ((nmax * lda + 3) & ~3) + 3 * ((nmax + 3) & ~3) + kMaxDim;
 }
 
 __device__ void carve_scratch(float*& p, int nmax, int ld, Scratch& S) {
-  S.Wst = bump(p, kMaxDim * kMaxDim);
+  S.Wst = nullptr;
   S.vb = bump(p, kMaxDim);
   S.va = bump(p, kMaxDim);
   S.vb2 = bump(p, kMaxDim);
@@ -325,13 +327,24 @@ __device__ void carve_scratch(float*& p, int nmax, int ld, Scratch& S) {
   S.AGG = nullptr;
 }
 
+// layer output buffer B1 and AGG, contiguous, padded so that the pair also holds the staged attention projection
+__host__ __device__ inline int layer_buffer_floats(int nmax, int ld) {
+  return max(2 * nmax * ld, kMaxDim * kMaxDim);
+}
+__device__ float* carve_layer_buffers(float*& p, int nmax, int ld, Scratch& S) {
+  float* region = bump(p, layer_buffer_floats(nmax, ld));
+  S.Wst = region;
+  S.AGG = region + nmax * ld;
+  return region;                          // B1
+}
+
 // ---------------------------------------------------------------------------------------
 // AASIST graph tail (AASIST.py:841-921)
 // ---------------------------------------------------------------------------------------
 __host__ __device__ inline int aasist_graph_smem_floats(int nmax, int ld, int nS, int nT, int nS2,
                                                         int nT2) {
-  int rows = 3 * nmax + (nT2 + nS2) + nS + nT + (nT2 + nS2);
-  return scratch_floats(nmax) + rows * ld + 4 * kMaxDim + 64;
+  int rows = nmax + (nT2 + nS2) + nS + nT + (nT2 + nS2);
+  return scratch_floats(nmax) + layer_buffer_floats(nmax, ld) + rows * ld + 4 * kMaxDim + 64;
 }
 
 __global__ void __launch_bounds__(kGraphThreads)
@@ -342,8 +355,7 @@ aasist_graph_kernel(const GraphArgsAasist a) {
   carve_scratch(p, a.nmax, a.ld, S);
   const int ld = a.ld;
   float* B0 = bump(p, a.nmax * ld);
-  float* B1 = bump(p, a.nmax * ld);
-  S.AGG = bump(p, a.nmax * ld);
+  float* B1 = carve_layer_buffers(p, a.nmax, ld, S);
   float* B3 = bump(p, (a.nT2 + a.nS2) * ld);     // pooled hetero nodes: T rows then S rows
   float* OS = bump(p, a.nS * ld);
   float* OT = bump(p, a.nT * ld);
@@ -491,7 +503,7 @@ int launch_graph_aasist(aasist_handle* h, const float* e, int B, int NT, float* 
 // RawGAT-ST graph tail (RawNetGatSpoofST.py:338-356)
 // ---------------------------------------------------------------------------------------
 __host__ __device__ inline int rawgat_graph_smem_floats(int nmax, int ld) {
-  return scratch_floats(nmax) + (3 * nmax + 2 * 12 + 12 + 12) * ld + 64;
+  return scratch_floats(nmax) + layer_buffer_floats(nmax, ld) + (nmax + 2 * 12 + 12 + 12) * ld + 64;
 }
 
 __global__ void __launch_bounds__(kGraphThreads)
@@ -502,8 +514,7 @@ rawgat_graph_kernel(const GraphArgsRawGat a) {
   carve_scratch(p, a.nmax, a.ld, S);
   const int ld = a.ld;
   float* B0 = bump(p, a.nmax * ld);
-  float* B1 = bump(p, a.nmax * ld);
-  S.AGG = bump(p, a.nmax * ld);
+  float* B1 = carve_layer_buffers(p, a.nmax, ld, S);
   float* PT = bump(p, 12 * ld);   // proj_T output as 12 nodes x 32 features
   float* PS = bump(p, 12 * ld);
   float* G = bump(p, 12 * ld);
