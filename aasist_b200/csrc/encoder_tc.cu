@@ -55,8 +55,10 @@ struct ConvTcParams {
   // Work items: B * n_full regular strips (128 columns each), then n_tail packed tiles.  The last, partial strip
   // of a row ("tail": rows - 128*n_full columns) is short in the deeper blocks; when it fits a 64-row segment,
   // `segs` utterances' tails share one 128-row tile, each in a `seg_rows`-row segment (columns 128*n_full - 1 ..,
-  // a multiple of 8 rows so the swizzle atoms line up).  n_tail == 0: every strip is regular.
-  int n_full, segs, seg_rows, n_tail, n_strips;
+  // a multiple of 8 rows so the swizzle atoms line up).  A tail wider than one segment is cut into `pieces` equal
+  // pieces of `piece_cols` columns, one segment each (block 4 at 4 s: 90 columns = 3 x 30, four segments per tile =
+  // 0.75 tiles per utterance instead of one).  n_tail == 0: every strip is regular.
+  int n_full, segs, seg_rows, pieces, piece_cols, n_tail, n_strips;
   const float* bias;       // [COP]
   __half* out;             // CONV1: [B][24][3][J][2*COP]; CONV2: [B][23][3][Jn][2*COP]
   float* out_f32;          // last block: (B,Co,23,Wo) fp32 NCHW (then `out` is unused)
@@ -251,9 +253,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       const int n_regular = p.B * p.n_full;
       for (int t = blockIdx.x; t < n_strips; t += gridDim.x) {
-        const bool tail = t >= n_regular;                          // packed tile of `segs` tails
-        const int b = tail ? (t - n_regular) * p.segs : t / p.n_full;
-        const int nseg = tail ? min(p.segs, p.B - b) : 1;          // utterances in this tile
+        const bool tail = t >= n_regular;                          // packed tile of `segs` tail pieces
+        const int q0 = tail ? (t - n_regular) * p.segs : 0;        // first (utterance, piece) of a packed tile
+        const int b = tail ? 0 : t / p.n_full;
+        const int nseg = tail ? min(p.segs, p.B * p.pieces - q0) : 1;   // segments in this tile
         const int j0 = (tail ? p.n_full : t % p.n_full) * kTileJ - 1;
         const uint32_t box_bytes = (uint32_t)(tail ? p.seg_rows : kBoxRows) * 128u;
         const CUtensorMap* mA = tail ? &tmAt : &tmA;
@@ -263,19 +266,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(&empty[slot], phase ^ 1);
             uint8_t* dst = s_ring + (size_t)slot * SLOT_BYTES;
             mbar_arrive_expect_tx(&full[slot], SLABS * nseg * box_bytes);
-            for (int g = 0; g < nseg; ++g)
+            for (int g = 0; g < nseg; ++g) {
+              const int bg = tail ? (q0 + g) / p.pieces : b;
+              const int jg = tail ? j0 + ((q0 + g) % p.pieces) * p.piece_cols : j0;
 #pragma unroll
               for (int sl = 0; sl < SLABS; ++sl)
-                tma_load_5d(dst + sl * kSlabBytes + (size_t)g * box_bytes, mA, &full[slot], sl * 64, j0, phi, r, b + g);
+                tma_load_5d(dst + sl * kSlabBytes + (size_t)g * box_bytes, mA, &full[slot], sl * 64, jg, phi, r, bg);
+            }
             if (++slot == p.n_slots) { slot = 0; phase ^= 1; }
           }
           if (HAS_SIDE && r < 23) {   // conv_downsample input: block input row h = r (output row r)
             for (int phi = 0; phi < 3; ++phi) {
               mbar_wait(&empty[slot], phase ^ 1);
               mbar_arrive_expect_tx(&full[slot], nseg * box_bytes);
-              for (int g = 0; g < nseg; ++g)
-                tma_load_5d(s_ring + (size_t)slot * SLOT_BYTES + (size_t)g * box_bytes, mS, &full[slot], 0, j0, phi, r,
-                            b + g);
+              for (int g = 0; g < nseg; ++g) {
+                const int bg = tail ? (q0 + g) / p.pieces : b;
+                const int jg = tail ? j0 + ((q0 + g) % p.pieces) * p.piece_cols : j0;
+                tma_load_5d(s_ring + (size_t)slot * SLOT_BYTES + (size_t)g * box_bytes, mS, &full[slot], 0, jg, phi, r, bg);
+              }
               if (++slot == p.n_slots) { slot = 0; phase ^= 1; }
             }
           }
@@ -448,11 +456,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         b = t / p.n_full;
         j = jt * kTileJ + r;
       } else {                              // packed tile: accumulator row r = (utterance, column) of segment g
-        const int g = r / p.seg_rows;
+        const int g = r / p.seg_rows, lc = r - g * p.seg_rows;
+        const int q = (t - p.B * p.n_full) * p.segs + g;           // (utterance, piece)
         jt = p.n_full;
-        b = (t - p.B * p.n_full) * p.segs + g;
-        j = p.n_full * kTileJ + (r - g * p.seg_rows);
-        if (g >= p.segs || b >= p.B) { b = p.B - 1; j = 1 << 28; }   // no utterance here: every guard below fails
+        b = q / p.pieces;
+        j = p.n_full * kTileJ + (q % p.pieces) * p.piece_cols + lc;
+        // rows past the piece (the next piece's columns, halo rows) and empty segments: every guard below fails
+        if (g >= p.segs || b >= p.B || lc >= p.piece_cols) { b = p.B - 1; j = 1 << 28; }
       }
       for (int h = 0; h < p.H_out; ++h, ++tcount) {
         const int buf = tcount & 1;
@@ -901,18 +911,29 @@ static int run_block_tc(aasist_handle* h, int enc, int index, const __half* in_p
   // tile plans: columns a row's strips must cover (conv2 also writes the zero rows up to 3*Jn of the next block's
   // layout); regular 128-column strips, and a packed tile for the tails when a tail fits a 64-row segment
   const int rows1 = J, rows2 = std::max(J, std::min(3 * Jn, Wo + 2));
-  struct StripPlan { int n_full, segs, seg_rows, n_tail; };
+  struct StripPlan { int n_full, segs, seg_rows, pieces, piece_cols, n_tail; };
   auto plan_strips = [nb](int rows) {
     StripPlan sp;
     sp.n_full = rows / kTileJ;
     const int rem = rows - sp.n_full * kTileJ;
-    sp.segs = 1; sp.seg_rows = kTileJ; sp.n_tail = 0;
+    sp.segs = 1; sp.seg_rows = kTileJ; sp.pieces = 1; sp.piece_cols = kTileJ; sp.n_tail = 0;
     if (rem > 0) {
-      const int seg_rows = ((rem + 2 + 7) / 8) * 8;
-      if (seg_rows <= 64) {
-        sp.seg_rows = seg_rows;
-        sp.segs = kTileJ / seg_rows;
-        sp.n_tail = (nb + sp.segs - 1) / sp.segs;
+      // cut the tail into 1..4 equal pieces of one segment each; keep the cut that needs the fewest tiles per
+      // utterance, if it beats a regular strip (1 tile)
+      int best_num = 1, best_den = 1, best_p = 0, best_rows = 0;
+      for (int pc = 1; pc <= 4; ++pc) {
+        const int cols = (rem + pc - 1) / pc;
+        const int seg_rows = ((cols + 2 + 7) / 8) * 8;
+        if (seg_rows > 64) continue;
+        const int segs = kTileJ / seg_rows;
+        if (pc * best_den < best_num * segs) { best_num = pc; best_den = segs; best_p = pc; best_rows = seg_rows; }
+      }
+      if (best_p) {
+        sp.pieces = best_p;
+        sp.piece_cols = (rem + best_p - 1) / best_p;
+        sp.seg_rows = best_rows;
+        sp.segs = kTileJ / best_rows;
+        sp.n_tail = (nb * sp.pieces + sp.segs - 1) / sp.segs;
       } else {
         sp.n_full += 1;                                  // the tail is a strip like the others
       }
@@ -947,7 +968,8 @@ static int run_block_tc(aasist_handle* h, int enc, int index, const __half* in_p
     ConvTcParams p;
     memset(&p, 0, sizeof(p));
     p.B = nb; p.H_out = 24; p.J = J; p.W_in = W; p.Co = blk.co;
-    p.n_full = sp1.n_full; p.segs = sp1.segs; p.seg_rows = sp1.seg_rows; p.n_tail = sp1.n_tail;
+    p.n_full = sp1.n_full; p.segs = sp1.segs; p.seg_rows = sp1.seg_rows; p.pieces = sp1.pieces;
+    p.piece_cols = sp1.piece_cols; p.n_tail = sp1.n_tail;
     p.bias = blk.c1.bias; p.out = mid; p.wimg = blk.c1.wimg; p.wimg_bytes = blk.c1.wimg_bytes;
     if (blk.cpi == 32 && blk.cop == 32) rc = launch_conv<32, 32, TC_CONV1>(h, kConvNames[0][index], tmIn, tmIn, tmInT1, tmInT1, p, st);   // 32 -> 24 (AASIST-L)
     else if (blk.cpi == 32 && blk.cop == 64) rc = launch_conv<32, 64, TC_CONV1>(h, kConvNames[0][index], tmIn, tmIn, tmInT1, tmInT1, p, st);
@@ -960,7 +982,8 @@ static int run_block_tc(aasist_handle* h, int enc, int index, const __half* in_p
   ConvTcParams p;
   memset(&p, 0, sizeof(p));
   p.B = nb; p.H_out = 23; p.J = J; p.W_in = W; p.Co = blk.co; p.Wo = Wo; p.Jn = Jn;
-  p.n_full = sp2.n_full; p.segs = sp2.segs; p.seg_rows = sp2.seg_rows; p.n_tail = sp2.n_tail;
+  p.n_full = sp2.n_full; p.segs = sp2.segs; p.seg_rows = sp2.seg_rows; p.pieces = sp2.pieces;
+  p.piece_cols = sp2.piece_cols; p.n_tail = sp2.n_tail;
   p.bias = blk.c2.bias; p.out = out_pairs; p.out_f32 = out_f32; p.wimg = blk.c2.wimg; p.wimg_bytes = blk.c2.wimg_bytes;
   if (!blk.downsample) {
     p.idn = in_pairs;   // 64 -> 64 identity block (the 32 -> 32 ones took the fused path above)
