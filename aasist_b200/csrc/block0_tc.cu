@@ -4,10 +4,12 @@
 //   z (B,23,W) fp32  --conv1 k(2,3) pad(1,1) + bn2 + SELU-->  v (32 ch, 24 rows)   [never leaves the SM]
 //                    --conv2 k(2,3) pad(0,1) + conv_downsample(z) k(1,3) + max-pool 3-->  pairs [B][23][3][Jn][64]
 //
-// conv1 has ONE input channel (K = 6 taps): as an MMA it is a single K=16 chunk whose A operand is an
-// im2col tile of z in fp16 pairs, [z_hi taps(6) | z_lo taps(6) | 0(4)], built by two producer warps;
-// B1 = [w_hi(6) | w_hi(6) | 0], B1' = [w_lo(6) | 0] give the three split products in two MMAs.
-// Its accumulator D1 (128 x 32, TMEM) is turned into conv2's A operand by 8 "transformer" warps:
+// conv1 has ONE input channel (6 taps): as an MMA its A operand is an im2col tile of z in fp16 pairs built by
+// three producer warps.  One tile serves all THREE pool phases of a v row: a row holds the five z columns
+// 3jj .. 3jj+4 of both input rows, K = 32 = [up_hi(5) dn_hi(5) 1 0(5) | up_lo(5) dn_lo(5) 0(6)], and the B
+// operands place each phase's taps on the columns it reads (N = 3 x 32): three N=96 MMAs per v row --
+// hi*w_hi (+ bias_hi on the constant-1 column), lo*w_hi, hi*w_lo (+ bias_lo) -- instead of six N=32 ones.
+// Its accumulator D1 (128 x 96, TMEM) is turned into conv2's A operand by 8 "transformer" warps:
 // tcgen05.ld -> +bias -> SELU -> zero outside [0,W) -> fp16 hi/lo -> 128B-swizzled rows of the same
 // shared-memory ring the TMA would fill for the later blocks.  conv2 then runs exactly like
 // conv_tc_kernel (strip-mined, two passes per input row, phase-split pooling), and conv_downsample
@@ -28,17 +30,18 @@ using namespace ptx;
 
 constexpr int kB0Strip = 126;               // valid pooled columns per strip
 constexpr int kB0Slab = 17 * 1024;          // one v tile (136 rows x 128 B, SWIZZLE_128B)
-constexpr int kB0A1Bytes = 17 * 256;        // im2col tile: 136 rows x 32 B, no-swizzle canonical
-constexpr int kB0A1Stride = 4608;
+constexpr int kB0A1Stride = 16 * 512;       // conv1 im2col tile of one v row: 128 rows x 64 B (K = 32), no-swizzle
+                                            // canonical: 8-row groups of 512 B = 4 K-groups x (8 rows x 16 B)
 constexpr int kB0DsBytes = 16 * 256;        // downsample im2col tile: 128 rows x 32 B
-constexpr int kB0NA1 = 8, kB0ND1 = 6, kB0NDS = 3;
+constexpr int kB0NA1 = 3, kB0ND1 = 3, kB0NDS = 3;   // rings of v rows (im2col tiles, D1 accumulators), downsample tiles
 constexpr int kB0Threads = 640;
 constexpr int kB0ZW = 400;                  // z columns kept per row: 3*j0-4 .. 3*j0+395 (392 used)
 constexpr int kB0W2Bytes = 6 * 32 * 128;    // conv2 weight image (6 taps x [32 rows x 128 B])
-constexpr int kB0ImgBytes = kB0W2Bytes + 2 * 1024 + 6 * 1024;   // + B1, B1' + 3 x (Bds, Bds')   (global image)
-// shared-memory image: conv2 in both slot orders (see block_fused_tc.cu), B1, B1', and the downsample operands
+constexpr int kB0B1Bytes = 3 * 3 * 1024;    // conv1 operands B1a, B1b, B1c: 96 rows x K=16 each
+constexpr int kB0ImgBytes = kB0W2Bytes + kB0B1Bytes + 6 * 1024;   // + 3 x (Bds, Bds')   (global image)
+// shared-memory image: conv2 in both slot orders (see block_fused_tc.cu), B1a/b/c, and the downsample operands
 // spread over the [phase][slot] accumulator columns with zero blocks for the other slot: [0,B0,0,B1,0,B2,0] x 2
-constexpr int kB0SmemImgBytes = 2 * kB0W2Bytes + 2 * 1024 + 2 * 7 * 1024;
+constexpr int kB0SmemImgBytes = 2 * kB0W2Bytes + kB0B1Bytes + 2 * 7 * 1024;
 
 struct Block0Params {
   const float* z;          // (B,23,W)
@@ -50,8 +53,8 @@ struct Block0Params {
   long long* stats;        // optional: per-CTA MMA-warp wait cycles [total, a1full, d1empty, vfull, tempty, dsfull]
 };
 
-__device__ __forceinline__ uint64_t b0_desc_noswz(uint32_t smem_addr) {   // LBO 128 B, SBO 256 B
-  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) |
+__device__ __forceinline__ uint64_t b0_desc_noswz(uint32_t smem_addr, uint32_t sbo = 256) {   // LBO 128 B
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
          ((uint64_t)1 << 46);
 }
 __device__ __forceinline__ float b0_ex2(float x) {
@@ -115,14 +118,14 @@ block0_tc_kernel(const Block0Params p) {
     reinterpret_cast<uint4*>(s_w)[i] =
         __ldg(reinterpret_cast<const uint4*>(p.wimg + (size_t)(((sigma ^ o) * 3 + tap) * 4096)) + within);
   }
-  for (int i = threadIdx.x; i < 2048 / 16; i += kB0Threads)     // B1, B1'
+  for (int i = threadIdx.x; i < kB0B1Bytes / 16; i += kB0Threads)     // B1a, B1b, B1c
     reinterpret_cast<uint4*>(s_w + 2 * kB0W2Bytes)[i] = __ldg(reinterpret_cast<const uint4*>(p.wimg + kB0W2Bytes) + i);
   for (int i = threadIdx.x; i < 2 * 7 * 1024 / 16; i += kB0Threads) {   // downsample: [0,B0,0,B1,0,B2,0] hi, then lo
     const int blk = i >> 6, within = i & 63;
     const int part = blk / 7, k = blk % 7;
     uint4 v = make_uint4(0, 0, 0, 0);
-    if (k & 1) v = __ldg(reinterpret_cast<const uint4*>(p.wimg + kB0W2Bytes + 2048 + (size_t)((part * 3 + (k >> 1)) * 1024)) + within);
-    reinterpret_cast<uint4*>(s_w + 2 * kB0W2Bytes + 2048)[i] = v;
+    if (k & 1) v = __ldg(reinterpret_cast<const uint4*>(p.wimg + kB0W2Bytes + kB0B1Bytes + (size_t)((part * 3 + (k >> 1)) * 1024)) + within);
+    reinterpret_cast<uint4*>(s_w + 2 * kB0W2Bytes + kB0B1Bytes)[i] = v;
   }
   // rows 128..135 of a v tile are read (by discarded accumulator rows) but never written: keep them finite
   for (int i = threadIdx.x; i < p.n_slots * kB0Slab / 16; i += kB0Threads)
@@ -145,7 +148,8 @@ block0_tc_kernel(const Block0Params p) {
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
-  // TMEM: [0,192) conv2 accumulators, column = s*64 + slot*32 + channel; [192,384) D1 ring (one 32-column tile each)
+  // TMEM: [0,192) conv2 accumulators, column = s*64 + slot*32 + channel; [192,480) D1 ring: three v rows of
+  // 96 columns (phase s at 32*s)
   constexpr int D1_COL0 = 192;
   if (warp >= 2 && warp < 10) {            // conv2 accumulators start at zero and return to zero after every drain
     const uint32_t tz = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(((warp - 2) >> 2) * 96);
@@ -165,30 +169,31 @@ block0_tc_kernel(const Block0Params p) {
     if (leader) {
     const uint32_t w_base = smem_u32(s_w), ring_base = smem_u32(s_ring);
     const uint32_t a1_base = smem_u32(s_a1), ds_base = smem_u32(s_ds);
-    const uint32_t b1_addr = w_base + 2 * kB0W2Bytes, b1p_addr = b1_addr + 1024, bds_addr = b1_addr + 2048;
-    constexpr uint32_t IDESC = umma_idesc_f16(128, 32);
-    int n1 = 0;                            // conv1 tiles issued
+    const uint32_t b1_addr = w_base + 2 * kB0W2Bytes, bds_addr = b1_addr + kB0B1Bytes;
+    int n1 = 0;                            // conv1 rows issued
     int slot = 0;
     uint32_t phase = 0;
     int g2 = 0, nds = 0;                   // conv2 steps issued (step g starts an output row in slot g & 1)
     long long w_a1 = 0, w_d1 = 0, w_vf = 0, w_te = 0, w_ds = 0;
     const long long t_begin = AASIST_CLOCK();
 
-    auto issue_conv1_row = [&]() {         // the three phase tiles of one v row
-      for (int phi = 0; phi < 3; ++phi, ++n1) {
-        const int ka = n1 % kB0NA1, kd = n1 % kB0ND1;
-        AASIST_TIMED_WAIT(&a1full[ka], (n1 / kB0NA1) & 1, w_a1);
-        AASIST_TIMED_WAIT(&d1empty[kd], ((n1 / kB0ND1) & 1) ^ 1, w_d1);
-        tc_fence_after_sync();
-        {
-          const uint64_t a = b0_desc_noswz(a1_base + (uint32_t)(ka * kB0A1Stride));
-          const uint32_t d = tmem_base + (uint32_t)(D1_COL0 + 32 * kd);
-          umma_f16(d, a, b0_desc_noswz(b1_addr), IDESC, 0);
-          umma_f16(d, a, b0_desc_noswz(b1p_addr), IDESC, 1);
-          umma_commit(&a1empty[ka]);
-          umma_commit(&d1full[kd]);
-        }
+    auto issue_conv1_row = [&]() {         // one v row: all three pool phases in three N=96 MMAs
+      const int ka = n1 % kB0NA1, kd = n1 % kB0ND1;
+      AASIST_TIMED_WAIT(&a1full[ka], (n1 / kB0NA1) & 1, w_a1);
+      AASIST_TIMED_WAIT(&d1empty[kd], ((n1 / kB0ND1) & 1) ^ 1, w_d1);
+      tc_fence_after_sync();
+      {
+        const uint32_t a_tile = a1_base + (uint32_t)(ka * kB0A1Stride);
+        const uint64_t a_hi = b0_desc_noswz(a_tile, 512), a_lo = b0_desc_noswz(a_tile + 256, 512);   // K slices 0, 1
+        const uint32_t d = tmem_base + (uint32_t)(D1_COL0 + 96 * kd);
+        constexpr uint32_t ID96 = umma_idesc_f16(128, 96);
+        umma_f16(d, a_hi, b0_desc_noswz(b1_addr), ID96, 0);                 // z_hi * w_hi + bias_hi
+        umma_f16(d, a_lo, b0_desc_noswz(b1_addr + 3 * 1024), ID96, 1);      // z_lo * w_hi
+        umma_f16(d, a_hi, b0_desc_noswz(b1_addr + 6 * 1024), ID96, 1);      // z_hi * w_lo + bias_lo
+        umma_commit(&a1empty[ka]);
+        umma_commit(&d1full[kd]);
       }
+      ++n1;
     };
     // conv2 MMAs of one v tile.  Pool phases that read the same A rows share one wider-N MMA, and so do the
     // two output rows the tile feeds (tap row dh=1 completes one, dh=0 starts the next): N = 64 / 128 / 192,
@@ -326,24 +331,21 @@ block0_tc_kernel(const Block0Params p) {
       const int j = jt * kB0Strip - 1 + jj;
       // warp-uniform: every row of this warp lies inside [0, W) for all three phases
       const bool valid_all = jt * kB0Strip - 1 + quad * 32 >= 0 && 3 * (jt * kB0Strip - 1 + quad * 32 + 31) + 2 < p.W;
-      for (int r = 0; r < 24; ++r, n += 3) {
+      for (int r = 0; r < 24; ++r, ++n) {
         uint32_t acc[3][16];
         {
-          const int kl = (n + 2) % kB0ND1;                       // commits arrive in order: the last tile's suffices
-          mbar_wait(&d1full[kl], ((n + 2) / kB0ND1) & 1);
+          const int kd = n % kB0ND1;
+          mbar_wait(&d1full[kd], (n / kB0ND1) & 1);
           tc_fence_after_sync();
 #pragma unroll
           for (int s = 0; s < 3; ++s)
-            tmem_ld16_async(tmem_base + ((uint32_t)(quad * 32) << 16) +
-                                (uint32_t)(D1_COL0 + 32 * ((n + s) % kB0ND1) + col0), acc[s]);
+            tmem_ld16_async(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(D1_COL0 + 96 * kd + 32 * s + col0),
+                            acc[s]);
 #pragma unroll
           for (int s = 0; s < 3; ++s) tmem_ld_wait16(acc[s]);
           tc_fence_before_sync();
           __syncwarp();
-          if (lane == 0) {
-#pragma unroll
-            for (int s = 0; s < 3; ++s) mbar_arrive(&d1empty[(n + s) % kB0ND1]);
-          }
+          if (lane == 0) mbar_arrive(&d1empty[kd]);
         }
         int sl[3];
 #pragma unroll
@@ -412,20 +414,16 @@ block0_tc_kernel(const Block0Params p) {
           }
         }
       };
-      // One pass builds everything that depends on z rows q-1 ("up") and q ("dn"): the three conv1 im2col tiles
-      // of v row q (tile row jj, phase phi: taps at window columns 3jj+phi .. +2 of both rows) and the
-      // conv_downsample tile of output row q-1 (row m = jj-1: window columns 3jj .. 3jj+4 of the up row).
-      // A thread reads the five (hi,lo) words of each row once and permutes them into the K=16 operand rows
-      //   conv1: [up_hi(3) dn_hi(3) up_lo(3) dn_lo(3) 1 0(3)]    downsample: [z_hi(5) z_lo(5) 0(6)]
+      // One pass builds everything that depends on z rows q-1 ("up") and q ("dn"): the conv1 im2col tile of v row q
+      // (tile row jj: window columns 3jj .. 3jj+4 of both rows serve all three pool phases) and the
+      // conv_downsample tile of output row q-1 (row m = jj-1: the same five columns of the up row).
+      // A thread reads the five (hi,lo) words of each row once and permutes them into the operand rows
+      //   conv1 (K=32): [up_hi(5) dn_hi(5) 1 0(5) | up_lo(5) dn_lo(5) 0(6)]    downsample (K=16): [z_hi(5) z_lo(5) 0(6)]
       auto row_pass = [&](int q) {
         const bool up = q >= 1, dn = q <= 22;
-        uint8_t* dst[3];
-#pragma unroll
-        for (int phi = 0; phi < 3; ++phi) {
-          const int ka = (n + phi) % kB0NA1;
-          mbar_wait(&a1empty[ka], (((n + phi) / kB0NA1) & 1) ^ 1);
-          dst[phi] = s_a1 + ka * kB0A1Stride;
-        }
+        const int ka = n % kB0NA1;
+        mbar_wait(&a1empty[ka], ((n / kB0NA1) & 1) ^ 1);
+        uint8_t* dst = s_a1 + ka * kB0A1Stride;
         uint8_t* dds = nullptr;
         if (up) {
           const int kq = nds % kB0NDS;
@@ -444,15 +442,12 @@ block0_tc_kernel(const Block0Params p) {
           auto hh = [](uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x5410); };   // (a.hi, b.hi)
           auto ll = [](uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x7632); };   // (a.lo, b.lo)
           if (jj < 128) {
-            const uint32_t roff = (uint32_t)((jj >> 3) * 256 + (jj & 7) * 16);
-#pragma unroll
-            for (int phi = 0; phi < 3; ++phi) {
-              uint8_t* row = dst[phi] + roff;
-              *reinterpret_cast<uint4*>(row) = make_uint4(hh(U[phi], U[phi + 1]), hh(U[phi + 2], D[phi]),
-                                                          hh(D[phi + 1], D[phi + 2]), ll(U[phi], U[phi + 1]));
-              *reinterpret_cast<uint4*>(row + 128) =
-                  make_uint4(ll(U[phi + 2], D[phi]), ll(D[phi + 1], D[phi + 2]), 0x00003C00u, 0u);   // k = 12: 1.0 (bias)
-            }
+            // K = 32 row: [up_hi(5) dn_hi(5) 1 0(5) | up_lo(5) dn_lo(5) 0(6)] as four 16-byte K-groups
+            uint8_t* row = dst + (jj >> 3) * 512 + (jj & 7) * 16;
+            *reinterpret_cast<uint4*>(row) = make_uint4(hh(U[0], U[1]), hh(U[2], U[3]), hh(U[4], D[0]), hh(D[1], D[2]));
+            *reinterpret_cast<uint4*>(row + 128) = make_uint4(hh(D[3], D[4]), 0x00003C00u, 0u, 0u);   // k = 10: 1.0
+            *reinterpret_cast<uint4*>(row + 256) = make_uint4(ll(U[0], U[1]), ll(U[2], U[3]), ll(U[4], D[0]), ll(D[1], D[2]));
+            *reinterpret_cast<uint4*>(row + 384) = make_uint4(ll(D[3], D[4]), 0u, 0u, 0u);
           }
           if (up && jj >= 1) {
             const int m = jj - 1;
@@ -465,11 +460,10 @@ block0_tc_kernel(const Block0Params p) {
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-#pragma unroll
-          for (int phi = 0; phi < 3; ++phi) mbar_arrive(&a1full[(n + phi) % kB0NA1]);
+          mbar_arrive(&a1full[ka]);
           if (up) mbar_arrive(&dsfull[nds % kB0NDS]);
         }
-        n += 3;
+        ++n;
         if (up) ++nds;
       };
       // same order as the MMA warp consumes: a1(row 0); then per r: a1(row r+1), ds(row r)
@@ -509,22 +503,28 @@ static void put_k16(std::vector<uint8_t>& img, size_t base, int n, int k, float 
   memcpy(&img[off], &v, 2);
 }
 
-// image = [conv2 weights (built by the caller, kB0W2Bytes)] [B1] [B1'] [Bds(s), Bds'(s)] x 3
+// image = [conv2 weights (built by the caller, kB0W2Bytes)] [B1a] [B1b] [B1c] [Bds(s), Bds'(s)] x 3
 void block0_pack_small(std::vector<uint8_t>& img, const std::vector<float>& w1 /*[6][32] bn folded*/,
                        const std::vector<float>& wd /*[3][32]*/, const std::vector<float>& bias1 /*[32] bn folded*/,
                        int co) {
   img.resize(kB0ImgBytes, 0);
-  const size_t b1 = kB0W2Bytes, b1p = b1 + 1024, bds = b1 + 2048;
+  const size_t b1a = kB0W2Bytes, b1b = b1a + 3 * 1024, b1c = b1b + 3 * 1024, bds = kB0W2Bytes + kB0B1Bytes;
   for (int o = 0; o < co; ++o) {
     // conv1 and its bias are scaled by log2(e): the transformers evaluate SELU from y = v * log2(e)
     const float bl = (float)((double)bias1[o] * 1.4426950408889634);
-    put_k16(img, b1, o, 12, bl, false);         // constant-1 column x bias_hi
-    put_k16(img, b1p, o, 12, bl, true);         //                   x bias_lo
-    for (int tp = 0; tp < 6; ++tp) {
-      const float w = (float)((double)w1[tp * 32 + o] * 1.4426950408889634);
-      put_k16(img, b1, o, tp, w, false);        // z_hi taps  x w_hi
-      put_k16(img, b1, o, 6 + tp, w, false);    // z_lo taps  x w_hi
-      put_k16(img, b1p, o, tp, w, true);        // z_hi taps  x w_lo
+    for (int s = 0; s < 3; ++s) {
+      const int n = 32 * s + o;                   // accumulator column: pool phase s, channel o
+      put_k16(img, b1a, n, 10, bl, false);        // constant-1 column x bias_hi
+      put_k16(img, b1c, n, 10, bl, true);         //                   x bias_lo
+      for (int dh = 0; dh < 2; ++dh)
+        for (int dw = 0; dw < 3; ++dw) {
+          // phase s reads window column 3jj + s + dw of input row dh: K index = 5*dh + s + dw
+          const float w = (float)((double)w1[(dh * 3 + dw) * 32 + o] * 1.4426950408889634);
+          const int k = 5 * dh + s + dw;
+          put_k16(img, b1a, n, k, w, false);      // z_hi x w_hi   (A K-slice 0)
+          put_k16(img, b1b, n, k, w, false);      // z_lo x w_hi   (A K-slice 1)
+          put_k16(img, b1c, n, k, w, true);       // z_hi x w_lo   (A K-slice 0)
+        }
     }
     // downsample tile columns: [z_hi(3j-1..3j+3) (5) | z_lo (5)]; pool phase s uses taps k = s .. s+2
     for (int s = 0; s < 3; ++s)
