@@ -330,14 +330,29 @@ static int pack_graph(aasist_handle* h) {
   return 0;
 }
 
-static int check_device(aasist_handle* h) {
-  int dev = -1;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice (no usable CUDA device; there is no CPU fallback)");
-  if (h && h->device < 0) h->device = dev;
-  if (h && dev != h->device) AASIST_CUDA(cudaSetDevice(h->device));
-  return 0;
-}
+// Makes the handle's device current for the duration of an entry point and restores the caller's
+// current device on exit (a handle on cuda:1 must not silently switch the thread to cuda:1).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  int enter(aasist_handle* h) {
+    cudaError_t e = cudaGetDevice(&prev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice (no usable CUDA device; there is no CPU fallback)");
+    if (h && h->device < 0) h->device = prev;
+    if (h && prev != h->device) {
+      AASIST_CUDA(cudaSetDevice(h->device));
+      switched = true;
+    }
+    return 0;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+#define AASIST_ENTER_DEVICE(h)        \
+  DeviceGuard _device_guard;          \
+  int rc = _device_guard.enter(h);    \
+  if (rc) return rc
 
 static inline int out_width(int L, int taps) { return (L - taps + 1) / 3; }
 
@@ -452,7 +467,8 @@ int aasist_create(const aasist_config* cfg, aasist_handle** out) {
 
 int aasist_destroy(aasist_handle* h) {
   if (!h) return AASIST_OK;
-  if (h->device >= 0) cudaSetDevice(h->device);
+  DeviceGuard guard;
+  if (h->device >= 0) guard.enter(h);
   cudaFree(h->bank);
   for (int e = 0; e < 2; ++e)
     for (int i = 0; i < 6; ++i) {
@@ -521,8 +537,7 @@ int aasist_set_param(aasist_handle* h, const char* name, const float* data, int6
 
 int aasist_finalize(aasist_handle* h) {
   if (!h) return AASIST_E_INVALID;
-  int rc = check_device(h);
-  if (rc) return rc;
+  AASIST_ENTER_DEVICE(h);
   for (auto& p : h->expected)
     if (!h->params.count(p.first)) {
       set_error("missing key in state_dict: \"%s\"", p.first.c_str());
@@ -618,8 +633,7 @@ int aasist_forward(aasist_handle* h, const float* x, int32_t B, int32_t L, float
     set_error("aasist_forward called before aasist_finalize");
     return AASIST_E_STATE;
   }
-  int rc = check_device(h);
-  if (rc) return rc;
+  AASIST_ENTER_DEVICE(h);
   Plan pl;
   if ((rc = make_plan(h, L, pl))) return rc;
   int64_t need = aasist_workspace_bytes(h, B, L);
@@ -665,8 +679,7 @@ int aasist_forward_host(aasist_handle* h, const float* x_host, int32_t B, int32_
     set_error("aasist_forward_host: invalid arguments");
     return AASIST_E_INVALID;
   }
-  int rc = check_device(h);
-  if (rc) return rc;
+  AASIST_ENTER_DEVICE(h);
   int64_t ws_bytes = aasist_workspace_bytes(h, B, L);
   if (ws_bytes < 0) return (int)ws_bytes;
   const int hd = aasist_hidden_dim(h);
@@ -760,8 +773,7 @@ int aasist_frontend(aasist_handle* h, const float* x, int32_t B, int32_t L, floa
     set_error("aasist_frontend: invalid arguments or handle not finalized");
     return AASIST_E_STATE;
   }
-  int rc = check_device(h);
-  if (rc) return rc;
+  AASIST_ENTER_DEVICE(h);
   Plan pl;
   if ((rc = make_plan(h, L, pl))) return rc;
   if (h->cfg.precision == AASIST_PREC_F16X3)
@@ -775,8 +787,7 @@ int aasist_encoder_block(aasist_handle* h, int32_t enc, int32_t index, const flo
     set_error("aasist_encoder_block: invalid arguments or handle not finalized");
     return AASIST_E_STATE;
   }
-  int rc = check_device(h);
-  if (rc) return rc;
+  AASIST_ENTER_DEVICE(h);
   if (h->cfg.precision == AASIST_PREC_F16X3)
     return tc_block_f32io(h, enc, index, in, B, W, out, workspace, workspace_bytes, (cudaStream_t)stream);
   const ConvBlockF32& blk = h->blocks[enc][index];
@@ -794,8 +805,7 @@ int aasist_graph(aasist_handle* h, const float* e, const float* e2, int32_t B, i
     set_error("aasist_graph: invalid arguments or handle not finalized");
     return AASIST_E_STATE;
   }
-  int rc = check_device(h);
-  if (rc) return rc;
+  AASIST_ENTER_DEVICE(h);
   if (h->cfg.kind == AASIST_KIND_AASIST)
     return launch_graph_aasist(h, e, B, NT, last_hidden, logits, topk_idx, pool_scores, (cudaStream_t)stream);
   if (!e2) {
@@ -818,8 +828,7 @@ int aasist_profile_report(aasist_handle* h, char* buf, int64_t buf_bytes, int32_
     set_error("aasist_profile_report: invalid arguments");
     return AASIST_E_INVALID;
   }
-  int rc = check_device(h);
-  if (rc) return rc;
+  AASIST_ENTER_DEVICE(h);
   AASIST_CUDA(cudaDeviceSynchronize());
   for (auto& sp : h->prof_pending) {
     float ms = 0.f;

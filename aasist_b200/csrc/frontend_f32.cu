@@ -135,12 +135,15 @@ int launch_frontend_f32(aasist_handle* h, const float* x, int B, int L, float* o
     return AASIST_E_INVALID;
   }
   size_t smem = sizeof(float) * (3 * n_bands * taps + 3 * kFrontTile + taps + 8);
-  static bool attr_set = false;
-  if (!attr_set) {
-    AASIST_CUDA(cudaFuncSetAttribute(sinc_frontend_f32_kernel,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    attr_set = true;
+  if (smem > 227 * 1024) {
+    // 3 * 23 * taps fp32 filter rows are resident per CTA: ~840 taps is the most that fits on an SM
+    set_error("first_conv=%d: a %d-tap filter bank needs %zu bytes of shared memory per CTA in the fp32 front end "
+              "(max 232448)", h->cfg.first_conv, taps, smem);
+    return AASIST_E_INVALID;
   }
+  // the attribute is per device (a second GPU in the same process needs it too): set it on every launch
+  AASIST_CUDA(cudaFuncSetAttribute(sinc_frontend_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
   dim3 grid((Wp + kFrontTile - 1) / kFrontTile, B);
   {
     LaunchSpan span(h, "sinc_frontend_f32", st);

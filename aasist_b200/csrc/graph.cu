@@ -243,7 +243,10 @@ __device__ void htrg_layer(const float* X1, int n1, const float* X2, int n2, int
 }
 
 // GraphPool.forward (AASIST.py:294-322): H (N,D) -> OUT (k,D) in descending score order.
-// Exact score ties go to the lower node index (torch leaves that order unspecified).
+// Nodes are ranked on the PRE-sigmoid weight w: sigmoid is monotone, so wherever the reference's fp32
+// sigmoid values differ strictly the order is the same as torch.topk's on the scores, and it does not
+// depend on the last ulp of any sigmoid implementation (a sigmoid collision of two different w is an
+// exact tie in the reference, whose order torch leaves unspecified).  Equal w go to the lower node index.
 __device__ void graph_pool(const float* H, int N, int ld, const PoolParams& P, int k, float* OUT,
                            int32_t* g_idx, float* g_wts, const Scratch& S) {
   for (int i = threadIdx.x; i < N; i += kGraphThreads) {
@@ -256,11 +259,11 @@ __device__ void graph_pool(const float* H, int N, int ld, const PoolParams& P, i
   }
   __syncthreads();
   for (int i = threadIdx.x; i < N; i += kGraphThreads) {
-    float si = S.sc[i];
+    float wi = S.wts[i];
     int r = 0;
     for (int j = 0; j < N; ++j) {
-      float sj = S.sc[j];
-      r += (sj > si) || (sj == si && j < i);
+      float wj = S.wts[j];
+      r += (wj > wi) || (wj == wi && j < i);
     }
     if (r < k) {
       S.idx[r] = i;

@@ -264,6 +264,9 @@ class _NativeModel(nn.Module):
         """x_host: CPU (ideally pinned) (B,L) fp32.  Returns CPU (last_hidden, output); the H2D
         copy, the forward and the D2H copy all run inside the C-ABI call."""
         lib = _lib.load()
+        if not isinstance(x_host, torch.Tensor) or x_host.is_cuda or x_host.dim() != 2:
+            raise RuntimeError("score_host expects a CPU tensor of shape (batch, samples); "
+                               "use forward() for tensors that already live on the device")
         dev = device or next(self.parameters()).device
         self._ensure_handle(dev)
         x_host = x_host.to(torch.float32).contiguous()
@@ -301,13 +304,20 @@ class _NativeModel(nn.Module):
                                             out.data_ptr(), stream))
         return out
 
+    def _require_handle(self) -> None:
+        if self._handle is None:
+            raise RuntimeError("the native handle does not exist yet: run a forward (or move the model to its "
+                               "CUDA device and call _ensure_handle) first")
+
     def profile(self, enable: bool = True) -> None:
         """Bracket every kernel launch with CUDA events on the launching stream."""
+        self._require_handle()
         _lib.check(_lib.load().aasist_profile_enable(self._handle, 1 if enable else 0))
 
     def profile_report(self, reset: bool = True):
         """[{kernel, launches, ms}] accumulated since the last reset (synchronises the device)."""
         import json
+        self._require_handle()
         buf = C.create_string_buffer(1 << 16)
         _lib.check(_lib.load().aasist_profile_report(self._handle, buf, len(buf), 1 if reset else 0))
         return json.loads(buf.value.decode())

@@ -73,7 +73,14 @@ def score_utterances(model, source: Union[Tensor, Callable[[int, int], Tensor]],
 def write_score_file(save_path: str, utt_ids: Sequence[str], scores: Iterable[float],
                      trial_lines: Sequence[str]) -> None:
     """Reference main.py:382-387: one ``"utt_id src key score"`` line per trial."""
-    scores = list(scores)
+    # the reference formats Python floats (`batch_score.tolist()`, main.py:377-380): a Tensor / ndarray
+    # (what score_utterances returns) is converted the same way, so "{}" never prints "tensor(...)"
+    if isinstance(scores, torch.Tensor):
+        scores = scores.detach().to(torch.float32).cpu().numpy().ravel().tolist()
+    elif hasattr(scores, "ravel") and hasattr(scores, "tolist"):
+        scores = scores.ravel().tolist()
+    else:
+        scores = [float(s) for s in scores]
     assert len(trial_lines) == len(utt_ids) == len(scores)
     with open(save_path, "w") as fh:
         for fn, sco, trl in zip(utt_ids, scores, trial_lines):

@@ -116,7 +116,7 @@ def run_with_taps(m, x, pools):
     return taps
 
 
-def pack(taps, x, bank, pools, enc_prefixes):
+def pack(taps, x, bank, pools, enc_prefixes, slim=False):
     out = {
         "x_head": x[:, :8].numpy(), "x_sum": x.double().sum(dim=1).numpy(),
         "bank": bank.numpy(),
@@ -134,7 +134,8 @@ def pack(taps, x, bank, pools, enc_prefixes):
             out[f"{pre}.{i}.absmean"] = e.abs().mean(dim=(1, 2, 3)).numpy()
         out[f"{pre}.5.full"] = taps[f"{pre}.5"].numpy()
     for k in taps:
-        if k.startswith("GAT_layer"):
+        # slim (long-utterance fixtures): keep the layer outputs, drop the (B,N,N,D) sub-module taps
+        if k.startswith("GAT_layer") and not (slim and "." in k):
             out[k] = taps[k].numpy()
     for p in pools:
         out[p + ".weights"] = taps[p + ".weights"].numpy()
@@ -170,6 +171,14 @@ def make_pad_golden():
     print("pad golden written")
 
 
+# BASELINE.json configs[4] (input-length sweep up to 256 000 samples = 116 temporal nodes)
+LONG_CASES = [
+    ("speech128k", O.speech_like, 2, 128000, 17),
+    ("speech192k", O.speech_like, 2, 192000, 19),
+    ("speech256k", O.speech_like, 2, 256000, 23),
+]
+
+
 def main():
     if "--only-pad" in sys.argv:
         return make_pad_golden()
@@ -182,21 +191,24 @@ def main():
         ("speech16k", O.speech_like, 2, 16000, 11),
         ("speech96k", O.speech_like, 2, 96000, 13),
     ]
+    only_long = "--only-long" in sys.argv        # add the long fixtures without rewriting the others
     summary = {}
     for name in ("AASIST", "AASIST-L"):
         m, mc = reference_aasist(name)
         nparam = sum(p.numel() for p in m.parameters())
         summary[name] = {"n_params": nparam}
         bank = m.conv_time.band_pass.clone()
-        for tag, gen, n, L, seed in cases:
+        for tag, gen, n, L, seed in (LONG_CASES if only_long else cases + LONG_CASES):
             x = gen(n, L, seed)
             taps = run_with_taps(m, x, POOLS)
-            d = pack(taps, x, bank, POOLS, ["encoder"])
+            d = pack(taps, x, bank, POOLS, ["encoder"], slim=L > 100000)
             d["meta"] = np.array(json.dumps({"model": name, "input": tag, "n": n, "L": L, "seed": seed,
                                              "n_params": nparam, "torch": torch.__version__,
                                              "numpy": np.__version__}))
             np.savez_compressed(os.path.join(GOLD, f"{name}_{tag}.npz"), **d)
             print(name, tag, "logits[0] =", taps["output"][0].tolist())
+    if only_long:
+        return
     m, mc = reference_rawgat()
     nparam = sum(p.numel() for p in m.parameters())
     summary["RawGAT-ST"] = {"n_params": nparam}

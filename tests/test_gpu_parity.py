@@ -15,7 +15,9 @@ pytestmark = pytest.mark.gpu
 
 LOGIT_TOL = 1e-4          # fp32 path: max-abs on logits / last_hidden (north_star: <= 1e-3)
 CASES = [("AASIST", "white"), ("AASIST", "speech"), ("AASIST", "speech16k"), ("AASIST", "speech96k"),
+         ("AASIST", "speech128k"), ("AASIST", "speech192k"), ("AASIST", "speech256k"),
          ("AASIST-L", "white"), ("AASIST-L", "speech"), ("AASIST-L", "speech16k"), ("AASIST-L", "speech96k"),
+         ("AASIST-L", "speech128k"), ("AASIST-L", "speech256k"),
          ("RawGAT-ST", "white"), ("RawGAT-ST", "speech")]
 
 
@@ -118,6 +120,8 @@ def test_full_forward_against_golden(name, tag):
     for p, r in rep.items():
         assert r["weights_err"] <= 1e-4, (p, r)
         assert r["mismatch_outside_near_ties"] == 0, (p, r)
+    if tag.startswith("speech"):
+        assert sum(r["strict_mismatch"] for r in rep.values()) == 0, rep
     print(json.dumps({"case": f"{name}/{tag}", "pools": rep}))
 
 

@@ -14,7 +14,9 @@ pytestmark = pytest.mark.gpu
 
 TC_LOGIT_TOL = 2e-4
 CASES = [("AASIST", "white"), ("AASIST", "speech"), ("AASIST", "speech16k"), ("AASIST", "speech96k"),
+         ("AASIST", "speech128k"), ("AASIST", "speech192k"), ("AASIST", "speech256k"),
          ("AASIST-L", "white"), ("AASIST-L", "speech"), ("AASIST-L", "speech16k"), ("AASIST-L", "speech96k"),
+         ("AASIST-L", "speech128k"), ("AASIST-L", "speech256k"),
          ("RawGAT-ST", "white"), ("RawGAT-ST", "speech")]
 
 
@@ -37,7 +39,7 @@ def test_tc_sinc_frontend_stage(name):
     assert err <= 2e-4 * max(1.0, ref.abs().max().item()), err
 
 
-@pytest.mark.parametrize("name", ["AASIST", "AASIST-L"])
+@pytest.mark.parametrize("name", ["AASIST", "AASIST-L", "RawGAT-ST"])
 def test_tc_encoder_blocks_stagewise(name):
     g = _g()
     x = O.speech_like(2, 64600, 4)
@@ -45,14 +47,16 @@ def test_tc_encoder_blocks_stagewise(name):
     m = g.native_model(name, "f16x3")
     f = O.CONFIGS[name]["filts"]
     chans = [f[1], f[2], f[3], f[4], f[4], f[4]]
-    inp = taps["frontend"]
     report = {}
-    for i in range(6):
-        ref = taps[f"encoder.{i}"]
-        out = g.stage_block(m, 0, i, inp.to(g.DEV), chans[i][1])
-        err = (out.cpu() - ref).abs().max().item()
-        report[i] = err / max(1.0, ref.abs().max().item())
-        inp = ref
+    # RawGAT-ST runs the same tensor-core kernels over two encoders with different weights
+    for e, pre in enumerate(["encoder_T", "encoder_S"] if name == "RawGAT-ST" else ["encoder"]):
+        inp = taps["frontend"]
+        for i in range(6):
+            ref = taps[f"{pre}.{i}"]
+            out = g.stage_block(m, e, i, inp.to(g.DEV), chans[i][1])
+            err = (out.cpu() - ref).abs().max().item()
+            report[f"{pre}.{i}"] = err / max(1.0, ref.abs().max().item())
+            inp = ref
     print(json.dumps({"model": name, "block_rel_err": report}))
     for i, e in report.items():
         # fp16-pair operands: ~2^-21 relative per product, fp32 accumulation
@@ -80,6 +84,65 @@ def test_tc_full_forward_against_golden(name, tag):
     for p, r in rep.items():
         assert r["weights_err"] <= 2e-4, (p, r)
         assert r["mismatch_outside_near_ties"] == 0, (p, r)
+    if tag.startswith("speech"):
+        # on speech-like input every ordered index equals the reference's wherever its
+        # neighbouring scores differ at all in fp32 (only exact ties may permute) -- on the path that ships
+        assert sum(r["strict_mismatch"] for r in rep.values()) == 0, rep
+
+
+def _tiled_golden(name, tag, B):
+    gold, meta = load_golden(name, tag)
+    x = golden_input(meta)
+    reps = (B + meta["n"] - 1) // meta["n"]
+    return gold, meta, x.repeat(reps, 1)[:B].contiguous()
+
+
+@pytest.mark.parametrize("name,B", [("AASIST", 640), ("AASIST", 1030), ("AASIST-L", 1030)])
+def test_tc_bench_batch_and_pass_boundary_against_golden(name, B):
+    """The benchmarked shape and beyond: B > 512 crosses the encoder-pass boundary (csrc/encoder_tc.cu processes
+    at most 512 utterances / 40 GB per pass).  The four golden speech utterances are tiled to B rows and EVERY row
+    is compared with the reference's golden logits, hidden vector and ordered GraphPool indices."""
+    g = _g()
+    gold, meta, x = _tiled_golden(name, "speech", B)
+    n = meta["n"]
+    m = g.native_model(name, "f16x3")
+    m.record_topk = True
+    try:
+        last_hidden, output = m(x.to(g.DEV))
+        torch.cuda.synchronize()
+        topk, weights = m.last_topk.clone(), m.last_pool_weights.clone()
+    finally:
+        m.record_topk = False
+    ref_out = np.tile(gold["output"], ((B + n - 1) // n, 1))[:B]
+    ref_hid = np.tile(gold["last_hidden"], ((B + n - 1) // n, 1))[:B]
+    err = np.abs(output.cpu().numpy() - ref_out).max()
+    herr = np.abs(last_hidden.cpu().numpy() - ref_hid).max()
+    print(json.dumps({"case": f"{name}/speech x{B}", "logit_err": float(err), "hidden_err": float(herr)}))
+    assert err <= TC_LOGIT_TOL and herr <= TC_LOGIT_TOL, (err, herr)
+    # every copy of an utterance scores bit-identically wherever it sits in the batch / pass
+    assert torch.equal(output[n:2 * n], output[:n])
+    for r in range(0, B - n + 1, n):
+        assert torch.equal(output[r:r + n], output[:n]), r
+        assert torch.equal(topk[r:r + n], topk[:n]), r
+    pools = g.split_pools(topk[:n], weights[:n], m.topk_layout(meta["L"]))
+    rep = g.check_pools(pools, gold, pools_of(name))
+    assert sum(r["strict_mismatch"] for r in rep.values()) == 0, rep
+
+
+@pytest.mark.parametrize("B,pinned", [(130, True), (130, False), (512, True), (512, False)])
+def test_tc_forward_host_two_piece_path_equals_device_forward(B, pinned):
+    """aasist_forward_host splits B > 128 into 128 + rest on two streams (csrc/api.cu) -- the path the bench's e2e
+    figure times: bit-equal to the device forward and within tolerance of the golden logits."""
+    g = _g()
+    gold, meta, x = _tiled_golden("AASIST", "speech", B)
+    m = g.native_model("AASIST", "f16x3")
+    lh_d, out_d = m(x.to(g.DEV))
+    xh = x.pin_memory() if pinned else x
+    lh_h, out_h = m.score_host(xh)
+    assert torch.equal(out_d.cpu(), out_h) and torch.equal(lh_d.cpu(), lh_h)
+    n = meta["n"]
+    ref_out = np.tile(gold["output"], ((B + n - 1) // n, 1))[:B]
+    assert np.abs(out_h.numpy() - ref_out).max() <= TC_LOGIT_TOL
 
 
 def test_tc_batch_invariance_and_fp32_agreement():

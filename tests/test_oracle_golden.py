@@ -8,7 +8,9 @@ from oracle import aasist_oracle as O
 from tests.util import golden_input, load_golden, load_sd, pools_of
 
 CASES = [("AASIST", "white"), ("AASIST", "speech"), ("AASIST", "speech16k"), ("AASIST", "speech96k"),
+         ("AASIST", "speech128k"), ("AASIST", "speech256k"),
          ("AASIST-L", "white"), ("AASIST-L", "speech"), ("AASIST-L", "speech16k"), ("AASIST-L", "speech96k"),
+         ("AASIST-L", "speech192k"),
          ("RawGAT-ST", "white"), ("RawGAT-ST", "speech")]
 
 

@@ -76,3 +76,19 @@ def test_score_file_format(tmp_path):
     p = tmp_path / "scores.txt"
     write_score_file(str(p), ["LA_E_1", "LA_E_2"], [-1.5, 2.25], trials)
     assert p.read_text() == "LA_E_1 A07 spoof -1.5\nLA_E_2 - bonafide 2.25\n"
+
+
+def test_score_file_accepts_the_tensor_score_utterances_returns(tmp_path):
+    """a Tensor / ndarray of scores must print as plain floats, like the reference's
+    `batch_score.tolist()` (main.py:377-380), so that calculate_tDCF_EER can parse the file."""
+    import numpy as np
+    trials = ["LA_0001 LA_E_1 - A07 spoof\n", "LA_0002 LA_E_2 - - bonafide\n"]
+    x = torch.tensor([[1.0, 1.0], [1.5, 0.0]])
+    scores = score_utterances(_StandIn(), x, 2, batch_size=1, device=torch.device("cpu"))
+    assert isinstance(scores, torch.Tensor)
+    for s in (scores, scores.numpy(), scores.double().numpy()):
+        p = tmp_path / "scores.txt"
+        write_score_file(str(p), ["LA_E_1", "LA_E_2"], s, trials)
+        assert p.read_text() == "LA_E_1 A07 spoof 1.0\nLA_E_2 - bonafide 1.125\n"
+        parsed = np.genfromtxt(str(p), dtype=str)           # what evaluation.py:26 does with the file
+        assert parsed[:, 3].astype(np.float64).tolist() == [1.0, 1.125]

@@ -12,7 +12,8 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 WDIR = os.path.join(ROOT, "aasist_b200", "weights")
 WEIGHTS = {"AASIST": "AASIST.pth", "AASIST-L": "AASIST-L.pth", "RawGAT-ST": "RawGATST_seed1234.pth"}
 GENERATORS = {"white": O.white_noise, "speech": O.speech_like,
-              "speech16k": O.speech_like, "speech96k": O.speech_like}
+              "speech16k": O.speech_like, "speech96k": O.speech_like, "speech128k": O.speech_like,
+              "speech192k": O.speech_like, "speech256k": O.speech_like}
 AASIST_POOLS = ["pool_S", "pool_T", "pool_hS1", "pool_hT1", "pool_hS2", "pool_hT2"]
 RAWGAT_POOLS = ["pool_T", "pool_S", "pool_ST"]
 
