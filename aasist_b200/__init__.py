@@ -3,11 +3,11 @@ utterance-scoring forward pass behind the reference's ``Model(d_args).forward(x)
 interface.  Host code is Python; all compute is hand-written CUDA in libaasist_b200.so,
 reached through the C ABI in include/aasist_b200.h.  No CPU fallback."""
 from .configs import CONFIGS, WEIGHTS, load_model_config, weights_path
-from .model import Model, RawGATSTModel
+from .model import Model, RawGATSTModel, RobustModel
 from .scoring import get_model, score_utterances, write_score_file
 
 # precisions whose kernels are built into libaasist_b200.so
 BUILT_PRECISIONS = ("fp32", "f16x3")
 
-__all__ = ["BUILT_PRECISIONS", "CONFIGS", "WEIGHTS", "Model", "RawGATSTModel", "get_model", "load_model_config",
+__all__ = ["BUILT_PRECISIONS", "CONFIGS", "WEIGHTS", "Model", "RawGATSTModel", "RobustModel", "get_model", "load_model_config",
            "score_utterances", "weights_path", "write_score_file"]

@@ -12,7 +12,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # AASIST_B200_LIB: developer override (kernel experiments build variant libraries next to the tree)
 LIB_PATH = os.environ.get("AASIST_B200_LIB") or os.path.join(_HERE, "csrc", "libaasist_b200.so")
 
-KIND_AASIST, KIND_RAWGAT_ST = 0, 1
+KIND_AASIST, KIND_RAWGAT_ST, KIND_ROBUST = 0, 1, 2
+ENC_RESIDUAL23, ENC_RES2NET, ENC_RESIDUAL33 = 0, 1, 2
+ABI_VERSION = 2
 PREC_FP32, PREC_F16X3 = 0, 1
 PRECISIONS = {"fp32": PREC_FP32, "f16x3": PREC_F16X3}
 
@@ -23,8 +25,16 @@ class AasistConfig(C.Structure):
         ("kind", C.c_int32), ("precision", C.c_int32), ("first_conv", C.c_int32),
         ("n_filters", C.c_int32), ("enc_channels", (C.c_int32 * 2) * 6),
         ("gat_dims", C.c_int32 * 2), ("pool_ratios", C.c_double * 4),
-        ("temperatures", C.c_double * 4), ("sample_rate", C.c_int32), ("reserved", C.c_int32 * 7),
+        ("temperatures", C.c_double * 4), ("sample_rate", C.c_int32), ("encoder", C.c_int32),
+        ("res2net_width", C.c_int32), ("res2net_scale", C.c_int32), ("spk_emb_dim", C.c_int32),
+        ("spk_level", C.c_int32), ("spk_use_attention", C.c_int32), ("reserved", C.c_int32 * 1),
     ]
+
+
+class ForwardOpts(C.Structure):
+    """Mirror of ``struct aasist_forward_opts``."""
+    _fields_ = [("speaker_embedding", C.c_void_p), ("freq_mask_start", C.c_int32), ("freq_mask_count", C.c_int32),
+                ("reserved", C.c_int32 * 4)]
 
 
 class AasistError(RuntimeError):
@@ -50,6 +60,15 @@ SIGNATURES = {
     "aasist_topk_layout": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "aasist_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "aasist_forward_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(ForwardOpts), C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "aasist_stage_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32),
+                                     C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_void_p,
+                                     C.c_void_p]),
+    "aasist_pad_sequence_length": (C.c_int32, [C.POINTER(C.c_int32), C.c_int32]),
+    "aasist_score_begin": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
+    "aasist_score_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
+    "aasist_score_finish": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "aasist_forward_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                       C.c_void_p, C.c_void_p]),
     "aasist_pad_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.c_int32,
@@ -85,7 +104,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.aasist_abi_version() != 1:
+    if lib.aasist_abi_version() != ABI_VERSION:
         raise ImportError("libaasist_b200.so ABI version mismatch; rebuild it")
     _lib = lib
     return lib

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libaasist_b200.so")
-SOURCES = ["api.cu", "frontend_f32.cu", "encoder_f32.cu", "graph.cu", "encoder_tc.cu", "frontend_tc.cu", "block0_tc.cu", "block_fused_tc.cu", "staging.cu", "metrics.cu"]
+SOURCES = ["api.cu", "frontend_f32.cu", "encoder_f32.cu", "encoder_res2.cu", "graph.cu", "encoder_tc.cu", "frontend_tc.cu", "block0_tc.cu", "block_fused_tc.cu", "staging.cu", "metrics.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
               "-Xptxas", "-v"]

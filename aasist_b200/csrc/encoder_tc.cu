@@ -786,7 +786,8 @@ int tc_finalize(aasist_handle* h) {
     return AASIST_E_CUDA;
   }
   const char* enc_names[2] = {h->cfg.kind == AASIST_KIND_AASIST ? "encoder" : "encoder_T", "encoder_S"};
-  for (int e = 0; e < h->n_encoders; ++e)
+  // the Res2Net encoder runs on fp32 kernels: only the sinc front end uses the tensor cores there
+  for (int e = 0; e < (h->cfg.encoder == AASIST_ENC_RESIDUAL23 ? h->n_encoders : 0); ++e)
     for (int i = 0; i < 6; ++i) {
       std::string p = std::string(enc_names[e]) + "." + std::to_string(i) + ".0";
       int rc = pack_block_tc(h, p, i, tc->blocks[e][i]);
@@ -995,7 +996,13 @@ static int run_block_tc(aasist_handle* h, int enc, int index, const __half* in_p
   return rc;
 }
 
-int tc_encode(aasist_handle* h, const float* x, int B, int L, float** enc_out, void* ws, cudaStream_t st) {
+int tc_encode(aasist_handle* h, const float* x, int B, int L, float** enc_out, void* ws, int mask_start,
+              int mask_count, cudaStream_t st) {
+  const uint8_t* bimg = h->tc->front_bimg;
+  if (mask_count > 0) {
+    int rc = tc_front_mask(h, bimg, mask_start, mask_count, st, &bimg);
+    if (rc) return rc;
+  }
   TcPlan pl;
   make_tc_plan(h, L, pl);
   const int nbmax = std::min(B, tc_chunk(pl.z + pl.mid + 2 * pl.act));
@@ -1014,8 +1021,8 @@ int tc_encode(aasist_handle* h, const float* x, int B, int L, float** enc_out, v
     const int nb = std::min(nbmax, B - b0);
     static int f32_front = -1;   // AASIST_TC_F32_FRONT=1: timing experiments with the CUDA-core sinc stage
     if (f32_front < 0) { const char* e = getenv("AASIST_TC_F32_FRONT"); f32_front = e ? atoi(e) : 0; }
-    int rc = f32_front ? launch_frontend_f32(h, x + (size_t)b0 * L, nb, L, z, st)
-                       : launch_frontend_tc(h, h->tc->front_bimg, h->tc->sm_count, x + (size_t)b0 * L, nb, L, z, st);
+    int rc = f32_front ? launch_frontend_f32(h, x + (size_t)b0 * L, nb, L, z, mask_start, mask_count, st)
+                       : launch_frontend_tc(h, bimg, h->tc->sm_count, x + (size_t)b0 * L, nb, L, z, st);
     if (rc) return rc;
     for (int e = 0; e < h->n_encoders; ++e) {
       const __half* in = nullptr;
@@ -1030,9 +1037,14 @@ int tc_encode(aasist_handle* h, const float* x, int B, int L, float** enc_out, v
   return 0;
 }
 
-int tc_frontend_to_f32(aasist_handle* h, const float* x, int B, int L, float* out, void*, int64_t,
+int tc_frontend_to_f32(aasist_handle* h, const float* x, int B, int L, float* out, int mask_start, int mask_count,
                        cudaStream_t st) {
-  return launch_frontend_tc(h, h->tc->front_bimg, h->tc->sm_count, x, B, L, out, st);
+  const uint8_t* bimg = h->tc->front_bimg;
+  if (mask_count > 0) {
+    int rc = tc_front_mask(h, bimg, mask_start, mask_count, st, &bimg);
+    if (rc) return rc;
+  }
+  return launch_frontend_tc(h, bimg, h->tc->sm_count, x, B, L, out, st);
 }
 
 int tc_block_f32io(aasist_handle* h, int enc, int index, const float* in, int B, int W, float* out, void* ws,

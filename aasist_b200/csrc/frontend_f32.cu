@@ -42,6 +42,14 @@ __global__ void sinc_filterbank_kernel(float* __restrict__ bank, int n_filters, 
   bank[idx] = __fmul_rn(window, (float)ideal);
 }
 
+__global__ void transpose_bank_kernel(const float* __restrict__ bank, float* __restrict__ bank_t, int n_filters,
+                                      int taps) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_filters * taps) return;
+  int f = idx / taps, k = idx % taps;
+  bank_t[k * n_filters + f] = bank[idx];
+}
+
 int build_filterbank(aasist_handle* h) {
   int n = h->cfg.n_filters * h->taps;
   if (!h->bank) AASIST_CUDA(cudaMalloc(&h->bank, sizeof(float) * n));
@@ -49,6 +57,12 @@ int build_filterbank(aasist_handle* h) {
                                                    h->cfg.sample_rate);
   h->launches++;
   AASIST_CUDA(cudaGetLastError());
+  if (h->cfg.kind == AASIST_KIND_ROBUST) {     // the strided front end reads the bank tap-major
+    if (!h->bank_t) AASIST_CUDA(cudaMalloc(&h->bank_t, sizeof(float) * n));
+    transpose_bank_kernel<<<(n + 127) / 128, 128>>>(h->bank, h->bank_t, h->cfg.n_filters, h->taps);
+    h->launches++;
+    AASIST_CUDA(cudaGetLastError());
+  }
   AASIST_CUDA(cudaDeviceSynchronize());
   return 0;
 }
@@ -65,7 +79,7 @@ constexpr int kFrontM = kFrontTile / kFrontTG;
 __global__ void __launch_bounds__(kSpecNodes* kFrontTG)
 sinc_frontend_f32_kernel(const float* __restrict__ x, const float* __restrict__ bank,
                          float* __restrict__ out, int L, int taps, int Wp, int n_bands,
-                         float bn_scale, float bn_shift) {
+                         float bn_scale, float bn_shift, int mask_start, int mask_count) {
   extern __shared__ float smem[];
   float* fs = smem;                               // [3*n_bands][taps]
   float* xs = smem + 3 * n_bands * taps;          // [3*kFrontTile + taps - 1 (+pad)]
@@ -73,7 +87,10 @@ sinc_frontend_f32_kernel(const float* __restrict__ x, const float* __restrict__ 
   const int p0 = blockIdx.x * kFrontTile;         // first pooled step of this tile
   const int t0 = 3 * p0;                          // first conv output time
   const int nx = 3 * kFrontTile + taps - 1;
-  for (int i = threadIdx.x; i < 3 * n_bands * taps; i += blockDim.x) fs[i] = bank[i];
+  for (int i = threadIdx.x; i < 3 * n_bands * taps; i += blockDim.x) {
+    const int f = i / taps;                       // Freq_aug (AASIST.py:486-490): masked filters are all-zero
+    fs[i] = (f >= mask_start && f < mask_start + mask_count) ? 0.f : bank[i];
+  }
   const float* xb = x + (size_t)b * L;
   for (int i = threadIdx.x; i < nx + 3; i += blockDim.x) {
     int g = t0 + i;
@@ -125,8 +142,8 @@ sinc_frontend_f32_kernel(const float* __restrict__ x, const float* __restrict__ 
   }
 }
 
-int launch_frontend_f32(aasist_handle* h, const float* x, int B, int L, float* out,
-                        cudaStream_t st) {
+int launch_frontend_f32(aasist_handle* h, const float* x, int B, int L, float* out, int mask_start,
+                        int mask_count, cudaStream_t st) {
   const int taps = h->taps;
   const int Wp = (L - taps + 1) / 3;
   const int n_bands = h->cfg.n_filters / 3;
@@ -148,7 +165,74 @@ int launch_frontend_f32(aasist_handle* h, const float* x, int B, int L, float* o
   {
     LaunchSpan span(h, "sinc_frontend_f32", st);
     sinc_frontend_f32_kernel<<<grid, n_bands * kFrontTG, smem, st>>>(
-        x, h->bank, out, L, taps, Wp, n_bands, h->bn0_scale, h->bn0_shift);
+        x, h->bank, out, L, taps, Wp, n_bands, h->bn0_scale, h->bn0_shift, mask_start, mask_count);
+  }
+  AASIST_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// AASIST-Robust front end (models/AASIST_Robust.py:96-102, 217-221): `first_conv` sinc filters of 1025 taps
+// at stride 256, then the same |.| -> 3x3 max-pool -> first_bn -> SELU.  0.07 MMAC per output frame and
+// filter: one CTA per (utterance, pooled step) = 3 frames x all filters, signal span (2*256 + taps samples)
+// in shared memory, bank read tap-major (coalesced over filters).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sinc_frontend_strided_f32_kernel(const float* __restrict__ x, const float* __restrict__ bank_t,
+                                 float* __restrict__ out, int L, int taps, int stride, int Wp, int n_filters,
+                                 int n_bands, float bn_scale, float bn_shift, int mask_start, int mask_count) {
+  extern __shared__ float smem[];
+  float* xs = smem;                                // [2*stride + taps]
+  float* ys = smem + 2 * stride + taps;            // [3 frames][3*n_bands] |conv|
+  const int b = blockIdx.y, p = blockIdx.x;
+  const int t0 = 3 * p * stride;                   // first sample of frame 3p
+  const int span = 2 * stride + taps;
+  const float* xb = x + (size_t)b * L;
+  for (int i = threadIdx.x; i < span; i += blockDim.x) xs[i] = (t0 + i < L) ? xb[t0 + i] : 0.f;
+  __syncthreads();
+  const int nf = 3 * n_bands;                      // filters that survive the floor-mode pool
+  for (int o = threadIdx.x; o < 3 * nf; o += blockDim.x) {
+    const int fr = o / nf, f = o % nf;
+    const float* xp = xs + fr * stride;
+    float acc = 0.f;
+    for (int k = 0; k < taps; ++k) acc = fmaf(xp[k], __ldg(bank_t + (size_t)k * n_filters + f), acc);
+    if (f >= mask_start && f < mask_start + mask_count) acc = 0.f;
+    ys[fr * nf + f] = fabsf(acc);
+  }
+  __syncthreads();
+  for (int band = threadIdx.x; band < n_bands; band += blockDim.x) {
+    float v = 0.f;
+#pragma unroll
+    for (int fr = 0; fr < 3; ++fr)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) v = fmaxf(v, ys[fr * nf + 3 * band + d]);
+    out[((size_t)b * n_bands + band) * Wp + p] = selu(fmaf(v, bn_scale, bn_shift));
+  }
+}
+
+int launch_frontend_strided_f32(aasist_handle* h, const float* x, int B, int L, float* out, int mask_start,
+                                int mask_count, cudaStream_t st) {
+  const int taps = h->taps, stride = h->stride;
+  if (L < taps) {
+    set_error("input length %d too short for a %d-tap filter bank", L, taps);
+    return AASIST_E_INVALID;
+  }
+  const int frames = (L - taps) / stride + 1;
+  const int Wp = frames / 3;
+  const int n_bands = h->cfg.n_filters / 3;
+  if (Wp < 1) {
+    set_error("input length %d gives %d frames: too short for the 3x3 max-pool", L, frames);
+    return AASIST_E_INVALID;
+  }
+  const size_t smem = sizeof(float) * (2 * stride + taps + 9 * n_bands + 8);
+  AASIST_CUDA(cudaFuncSetAttribute(sinc_frontend_strided_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+  dim3 grid(Wp, B);
+  {
+    LaunchSpan span(h, "sinc_frontend_strided_f32", st);
+    sinc_frontend_strided_f32_kernel<<<grid, 256, smem, st>>>(x, h->bank_t, out, L, taps, stride, Wp, h->cfg.n_filters,
+                                                              n_bands, h->bn0_scale, h->bn0_shift, mask_start,
+                                                              mask_count);
   }
   AASIST_CUDA(cudaGetLastError());
   return 0;

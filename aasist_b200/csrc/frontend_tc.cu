@@ -311,6 +311,35 @@ int tc_front_finalize(aasist_handle* h, uint8_t** bimg_dev) {
   return 0;
 }
 
+// Freq_aug (models/AASIST.py:486-490): copy of the filter operand image with the rows of the masked filters zeroed.
+// One thread per 16-byte unit; unit u of a K chunk holds row n = (u/16)*8 + u%8 (see tc_front_finalize).
+__global__ void mask_front_image_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int n_units,
+                                        int mask_start, int mask_count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_units) return;
+  const int u = i % (kFtBChunk / 16);
+  const int n = (u / 16) * 8 + (u % 8);
+  const int f = 3 * (n / 9) + (n % 9) / 3;
+  const bool masked = n < 9 * kSpecNodes && f >= mask_start && f < mask_start + mask_count;
+  dst[i] = masked ? make_uint4(0u, 0u, 0u, 0u) : src[i];
+}
+
+int tc_front_mask(aasist_handle* h, const uint8_t* bimg, int mask_start, int mask_count, cudaStream_t st,
+                  const uint8_t** out) {
+  const size_t bytes = (size_t)2 * kFtKC * kFtBChunk;
+  if (!h->front_bimg_masked) AASIST_CUDA(cudaMalloc(&h->front_bimg_masked, bytes));
+  const int n_units = (int)(bytes / 16);
+  {
+    LaunchSpan span(h, "freq_mask_filter_image", st);
+    mask_front_image_kernel<<<(n_units + 255) / 256, 256, 0, st>>>(reinterpret_cast<const uint4*>(bimg),
+                                                                  reinterpret_cast<uint4*>(h->front_bimg_masked),
+                                                                  n_units, mask_start, mask_count);
+  }
+  AASIST_CUDA(cudaGetLastError());
+  *out = h->front_bimg_masked;
+  return 0;
+}
+
 int launch_frontend_tc(aasist_handle* h, const uint8_t* bimg, int sm_count, const float* x, int B, int L,
                        float* out, cudaStream_t st) {
   const int Wp = (L - h->taps + 1) / 3;

@@ -347,7 +347,57 @@ __device__ float* carve_layer_buffers(float*& p, int nmax, int ld, Scratch& S) {
 __host__ __device__ inline int aasist_graph_smem_floats(int nmax, int ld, int nS, int nT, int nS2,
                                                         int nT2) {
   int rows = nmax + (nT2 + nS2) + nS + nT + (nT2 + nS2);
-  return scratch_floats(nmax) + layer_buffer_floats(nmax, ld) + rows * ld + 4 * kMaxDim + 64;
+  return scratch_floats(nmax) + layer_buffer_floats(nmax, ld) + rows * ld + 7 * kMaxDim + 64;
+}
+
+// SpeakerConditioningModule.forward, frame level (models/AASIST.py:384-403), in place on `n` rows of R
+// (all threads of the CTA).  sp = proj(emb) and u = fusion.weight[:, g1:] @ sp are precomputed per utterance.
+//   attention: a = softmax_rows( att2 . tanh(att0 [f_r ; sp]) ),  out_r = relu(fus [f_r ; a_r * sp])
+//   plain    :                                                     out_r = relu(fus [f_r ; sp])
+__device__ void speaker_condition_rows(float* R, int n, int ld, int g1, const SpkParams& P, const float* sp,
+                                       const float* u, float* tmp, const Scratch& S) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (P.use_attention) {
+    for (int r = warp; r < n; r += kWarps) {
+      float part = 0.f;
+      for (int k = lane; k < g1; k += 32) {
+        float pre = __ldg(P.att0B + k);
+        for (int d = 0; d < g1; ++d) pre = fmaf(R[r * ld + d], __ldg(P.att0Wt + d * g1 + k), pre);
+        for (int d = 0; d < g1; ++d) pre = fmaf(sp[d], __ldg(P.att0Wt + (g1 + d) * g1 + k), pre);
+        part = fmaf(__ldg(P.att2W + k), tanhf(pre), part);
+      }
+      part = warp_sum(part);
+      if (lane == 0) S.wts[r] = part + P.att2B;
+    }
+    __syncthreads();
+    if (warp == 0) {                                 // nn.Softmax(dim=1): over the rows (frames) of this set
+      float m = -INFINITY;
+      for (int j = lane; j < n; j += 32) m = fmaxf(m, S.wts[j]);
+      m = warp_max(m);
+      float s = 0.f;
+      for (int j = lane; j < n; j += 32) {
+        float e = expf(S.wts[j] - m);
+        S.wts[j] = e;
+        s += e;
+      }
+      s = warp_sum(s);
+      for (int j = lane; j < n; j += 32) S.wts[j] = S.wts[j] / s;
+    }
+    __syncthreads();
+  }
+  for (int t = threadIdx.x; t < n * g1; t += kGraphThreads) {
+    const int r = t / g1, k = t % g1;
+    float acc = __ldg(P.fusB + k);
+    for (int d = 0; d < g1; ++d) acc = fmaf(R[r * ld + d], __ldg(P.fusWt + d * g1 + k), acc);
+    acc += (P.use_attention ? S.wts[r] : 1.f) * u[k];
+    tmp[r * ld + k] = fmaxf(acc, 0.f);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < n * g1; t += kGraphThreads) {
+    const int r = t / g1, k = t % g1;
+    R[r * ld + k] = tmp[r * ld + k];
+  }
+  __syncthreads();
 }
 
 __global__ void __launch_bounds__(kGraphThreads)
@@ -367,6 +417,9 @@ aasist_graph_kernel(const GraphArgsAasist a) {
   float* m1 = bump(p, kMaxDim);
   float* m2 = bump(p, kMaxDim);
   float* m0 = bump(p, kMaxDim);
+  float* spv = bump(p, kMaxDim);                 // speaker projection
+  float* spu = bump(p, kMaxDim);                 // fusion.weight[:, g1:] @ speaker projection
+  float* emean = bump(p, kMaxDim);               // robust: mean of e over (freq, time) per channel
 
   // the grid is sized so that every CTA walks the same number of utterances (no partial last wave)
   for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
@@ -374,6 +427,17 @@ aasist_graph_kernel(const GraphArgsAasist a) {
   int32_t* gi = a.topk_idx ? a.topk_idx + (size_t)b * a.topk_total : nullptr;
   float* gw = a.pool_scores ? a.pool_scores + (size_t)b * a.score_total : nullptr;
 
+  if (a.robust) {                                                         // AASIST_Robust.py:227 e.mean(dim=(2,3))
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cnt = kSpecNodes * a.NT;
+    for (int c = warp; c < a.C; c += kWarps) {
+      float s = 0.f;
+      for (int i = lane; i < cnt; i += 32) s += e[(size_t)c * cnt + i];
+      s = warp_sum(s);
+      if (lane == 0) emean[c] = s / (float)cnt;
+    }
+    __syncthreads();
+  }
   // spectral graph                                                       (AASIST.py:841-845)
   nodes_max_over_time(e, a.C, a.NT, a.posS, B0, ld);
   gat_layer(B0, kSpecNodes, ld, a.gatS, B1, S);
@@ -389,7 +453,7 @@ aasist_graph_kernel(const GraphArgsAasist a) {
 
   float* PT = B3;
   float* PS = B3 + a.nT2 * ld;
-  for (int br = 0; br < 2; ++br) {                                       // :859-869 / :872-881
+  for (int br = 0; br < (a.robust ? 1 : 2); ++br) {                      // :859-869 / :872-881
     const HtrgParams& L1 = br == 0 ? a.st11 : a.st21;
     const HtrgParams& L2 = br == 0 ? a.st12 : a.st22;
     const PoolParams& pS = br == 0 ? a.poolhS1 : a.poolhS2;
@@ -418,9 +482,26 @@ aasist_graph_kernel(const GraphArgsAasist a) {
     }
     __syncthreads();
   }
+  const int g1 = a.g1;
+  if (a.spk_emb) {                                                       // :895-900, frame-level conditioning
+    const float* emb = a.spk_emb + (size_t)b * a.spk.emb_dim;
+    for (int k = threadIdx.x; k < g1; k += kGraphThreads) {
+      float s = __ldg(a.spk.projB + k);
+      for (int q = 0; q < a.spk.emb_dim; ++q) s = fmaf(__ldg(a.spk.projW + (size_t)k * a.spk.emb_dim + q), emb[q], s);
+      spv[k] = s;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < g1; k += kGraphThreads) {
+      float s = 0.f;
+      for (int d = 0; d < g1; ++d) s = fmaf(spv[d], __ldg(a.spk.fusWt + (g1 + d) * g1 + k), s);
+      spu[k] = s;
+    }
+    __syncthreads();
+    speaker_condition_rows(R, a.nT2, ld, g1, a.spk, spv, spu, B1, S);                 // out_T
+    speaker_condition_rows(R + a.nT2 * ld, a.nS2, ld, g1, a.spk, spv, spu, B1, S);    // out_S
+  }
   // readout (:903-910) + output layer (:919)
   float* lh = S.AGG;  // reuse: 5*g1 floats
-  const int g1 = a.g1;
   for (int k = threadIdx.x; k < g1; k += kGraphThreads) {
     float tmax = 0.f, tsum = 0.f, smax = 0.f, ssum = 0.f;
     for (int r = 0; r < a.nT2; ++r) {
@@ -440,14 +521,22 @@ aasist_graph_kernel(const GraphArgsAasist a) {
     lh[4 * g1 + k] = Rm[k];
   }
   __syncthreads();
-  for (int k = threadIdx.x; k < 5 * g1; k += kGraphThreads)
-    a.last_hidden[(size_t)b * 5 * g1 + k] = lh[k];
+  const int nh = (a.robust ? 4 : 5) * g1;       // AASIST_Robust.py:283 drops the master node from the readout
+  if (!a.robust)
+    for (int k = threadIdx.x; k < nh; k += kGraphThreads) a.last_hidden[(size_t)b * nh + k] = lh[k];
   if (threadIdx.x < 64) {
     const int lane = threadIdx.x & 31, o = threadIdx.x >> 5;
     float s = 0.f;
-    for (int k = lane; k < 5 * g1; k += 32) s = fmaf(lh[k], __ldg(a.outWt + k * 2 + o), s);
+    for (int k = lane; k < nh; k += 32) s = fmaf(lh[k], __ldg(a.outWt + k * 2 + o), s);
     s = warp_sum(s);
-    if (lane == 0) a.logits[(size_t)b * 2 + o] = s + (o == 0 ? a.outB0 : a.outB1);
+    const float logit = s + (o == 0 ? a.outB0 : a.outB1);
+    if (a.robust) {                             // aux head on mean(e) and the ensemble (:290-301)
+      float x = 0.f;
+      for (int c = lane; c < a.C; c += 32) x = fmaf(emean[c], __ldg(a.auxWt + c * 2 + o), x);
+      x = warp_sum(x) + (o == 0 ? a.auxB0 : a.auxB1);
+      if (lane == 0) a.last_hidden[(size_t)b * 2 + o] = a.ens0 * logit + a.ens1 * x;
+    }
+    if (lane == 0) a.logits[(size_t)b * 2 + o] = logit;
   }
   __syncthreads();   // shared buffers are reused by the next utterance
   }
@@ -466,15 +555,17 @@ static int balanced_grid(Kernel kern, int B, size_t smem, int device) {
   return (B + waves - 1) / waves;
 }
 
-int launch_graph_aasist(aasist_handle* h, const float* e, int B, int NT, float* last_hidden,
+int launch_graph_aasist(aasist_handle* h, const float* e, int B, int NT, const float* spk_emb, float* last_hidden,
                         float* logits, int32_t* topk, float* scores, cudaStream_t st) {
   GraphArgsAasist a = h->ga;
   const aasist_config& c = h->cfg;
   a.NT = NT;
+  a.spk_emb = spk_emb;
   a.nS = pooled_count(kSpecNodes, c.pool_ratios[0], 1);
   a.nT = pooled_count(NT, c.pool_ratios[1], 1);
   a.nS2 = pooled_count(a.nS, c.pool_ratios[2], 1);
-  a.nT2 = pooled_count(a.nT, c.pool_ratios[2], 1);
+  // AASIST: both hetero pools use pool_ratios[2] (AASIST.py:796-802); Robust: pool_hT uses [3] (AASIST_Robust.py:179-183)
+  a.nT2 = pooled_count(a.nT, c.pool_ratios[a.robust ? 3 : 2], 1);
   a.nmax = max(max(NT, kSpecNodes), a.nT + a.nS);
   int dmax = max(max(a.C, a.g0), a.g1);
   a.ld = dmax | 1;
@@ -483,8 +574,9 @@ int launch_graph_aasist(aasist_handle* h, const float* e, int B, int NT, float* 
   a.logits = logits;
   a.topk_idx = topk;
   a.pool_scores = scores;
-  a.topk_total = a.nS + a.nT + 2 * (a.nS2 + a.nT2);
-  a.score_total = kSpecNodes + NT + 2 * (a.nS + a.nT);
+  const int nbr = a.robust ? 1 : 2;
+  a.topk_total = a.nS + a.nT + nbr * (a.nS2 + a.nT2);
+  a.score_total = kSpecNodes + NT + nbr * (a.nS + a.nT);
   size_t smem = sizeof(float) * (size_t)aasist_graph_smem_floats(a.nmax, a.ld, a.nS, a.nT, a.nS2, a.nT2);
   if (smem > 227 * 1024) {
     set_error("utterance too long for the on-chip graph stage: %d temporal nodes need %zu bytes "

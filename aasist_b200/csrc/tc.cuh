@@ -10,9 +10,13 @@ int tc_finalize(aasist_handle* h);
 void tc_destroy(aasist_handle* h);
 size_t tc_workspace_bytes(const aasist_handle* h, int B, int L);
 // x (B,L) -> enc_out[e] (B,C,23,NT) fp32 NCHW for every encoder of the model
-int tc_encode(aasist_handle* h, const float* x, int B, int L, float** enc_out, void* ws, cudaStream_t st);
-int tc_frontend_to_f32(aasist_handle* h, const float* x, int B, int L, float* out, void* ws,
-                       int64_t ws_bytes, cudaStream_t st);
+// mask_count > 0: Freq_aug, filters [mask_start, mask_start+mask_count) are zero for this call
+int tc_encode(aasist_handle* h, const float* x, int B, int L, float** enc_out, void* ws, int mask_start,
+              int mask_count, cudaStream_t st);
+int tc_frontend_to_f32(aasist_handle* h, const float* x, int B, int L, float* out, int mask_start, int mask_count,
+                       cudaStream_t st);
+int tc_front_mask(aasist_handle* h, const uint8_t* bimg, int mask_start, int mask_count, cudaStream_t st,
+                  const uint8_t** out);
 int tc_block_f32io(aasist_handle* h, int enc, int index, const float* in, int B, int W, float* out,
                    void* ws, int64_t ws_bytes, cudaStream_t st);
 // tensor-core sinc front end (frontend_tc.cu)

@@ -41,9 +41,10 @@ def score_utterances(model, source: Union[Tensor, Callable[[int, int], Tensor]],
     """Score ``n_total`` utterances; returns the (n_total,) fp32 bona-fide logits ``output[:,1]``
     (reference main.py:377) on ``device`` -- identical on every rank and for every world size.
 
-    ``source`` is either an ``(n_total, L)`` tensor (CUDA, or CPU -- then each batch is copied
-    host->device like main.py:372) or a callable ``source(start, stop) -> (stop-start, L)`` CUDA
-    tensor.  With ``torch.distributed`` initialised, each rank scores its block and the scores
+    ``source`` is either an ``(n_total, L)`` tensor or a callable ``source(start, stop) -> (stop-start, L)``
+    tensor, on the device or on the HOST.  Host batches go through the library's scoring stream
+    (``aasist_score_begin/submit/finish``): pinned double-buffered staging, H2D of batch n+1 under the forward
+    of batch n, one device->host hop at the very end instead of main.py:372-377's per-batch round trip.  With ``torch.distributed`` initialised, each rank scores its block and the scores
     are exchanged with ONE all-gather (NCCL on GPUs; gloo in the CPU tests).
     """
     distributed = dist.is_available() and dist.is_initialized()
@@ -52,17 +53,31 @@ def score_utterances(model, source: Union[Tensor, Callable[[int, int], Tensor]],
     if device is None:
         device = next(model.parameters()).device
     start, stop, per = shard_bounds(n_total, world, rank)
-    # each rank's forward writes straight into its slice of the all-gather send buffer
+    # the all-gather send buffer: every rank contributes `per` scores (the last rank's tail stays zero)
     local = torch.zeros(per, dtype=torch.float32, device=device)
     model.eval()
+    first = None
+    if stop > start:
+        first = source(start, min(stop, start + batch_size)) if callable(source) else source[start:min(stop, start + batch_size)]
+    host_pipeline = first is not None and not first.is_cuda and hasattr(model, "score_begin") and device.type == "cuda"
     with torch.no_grad():
-        for b0 in range(start, stop, batch_size):
-            b1 = min(stop, b0 + batch_size)
-            x = source(b0, b1) if callable(source) else source[b0:b1]
-            if x.device != device:
-                x = x.to(device, non_blocking=True)
-            _, out = model(x)
-            local[b0 - start:b1 - start] = out[:, 1]
+        if host_pipeline:
+            # HOST utterances: two staging buffers, the H2D of batch n+1 runs under the forward of batch n, scores
+            # accumulate on the device and nothing waits until the end (replaces main.py:372-377's round trip)
+            model.score_begin(stop - start, batch_size, first.shape[-1], device)
+            for b0 in range(start, stop, batch_size):
+                b1 = min(stop, b0 + batch_size)
+                x = first if b0 == start else (source(b0, b1) if callable(source) else source[b0:b1])
+                model.score_submit(x)
+            local[:stop - start] = model.score_finish(on_device=True)[:, 1]
+        else:
+            for b0 in range(start, stop, batch_size):
+                b1 = min(stop, b0 + batch_size)
+                x = first if b0 == start else (source(b0, b1) if callable(source) else source[b0:b1])
+                if x.device != device:
+                    x = x.to(device, non_blocking=True)
+                _, out = model(x)
+                local[b0 - start:b1 - start] = out[:, 1]
     if not distributed:
         return local[:n_total]
     gathered = torch.empty(world * per, dtype=torch.float32, device=device)

@@ -6,7 +6,17 @@
 A "step" is one pass of the hot path (Model.forward) over one batch of synthetic 4 s / 16 kHz
 waveforms per GPU.  Workload at N=1 = BASELINE.json configs[1]: AASIST (config/AASIST.conf,
 models/weights/AASIST.pth), batch 512, L=64600.  N>1: every rank scores its own 512-utterance
-shard and the bona-fide scores are all-gathered over NCCL each step (weak scaling).
+shard; the bona-fide scores accumulate on the device and ONE NCCL all-gather at the end of the timed
+region collects them (weak scaling).
+
+Measurement layout of the native arm:
+  1. `value`   K forwards over inputs resident in HBM, timed with CUDA events, nothing else inside the region;
+  2. `e2e`     the same K batches from pinned HOST memory through the scoring stream
+               (aasist_score_begin/submit/finish: H2D of batch n+1 under the forward of batch n), with the final
+               device->host read of the scores inside the region;
+  3. an UNTIMED pass with per-launch CUDA events for the per-kernel table and the roofline of the dominant kernel;
+  4. baselines: the CPU oracle port (AASIST sample + BASELINE C1 = AASIST-L batch 24) and the oracle run eagerly
+     on the GPU in fp32 (the reference's real deployment; TF32 off).
 """
 from __future__ import annotations
 
@@ -42,6 +52,7 @@ def parse():
                          "71,237 synthetic utterances sharded across the ranks with one score all-gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true")
     args = ap.parse_args()
     global L_SAMPLES
     L_SAMPLES = args.samples
@@ -51,6 +62,32 @@ def parse():
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port (the reference is pure Python/torch, nothing compiles into oracle/_ref)
 # ------------------------------------------------------------------------------------------------
+def gpu_eager_throughput(model_name: str, dev, batch: int = 64, repeats: int = 3):
+    """The oracle's functional forward executed by torch on the GPU in fp32 with TF32 disabled -- what the
+    reference's own `main.py --eval` does on a CUDA device (cuDNN / cuBLAS kernels, ~250 launches per forward)."""
+    import torch
+    from oracle import aasist_oracle as O
+    import aasist_b200
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sd = {k: v.to(dev) for k, v in torch.load(aasist_b200.weights_path(model_name), map_location="cpu").items()}
+    cfg = O.CONFIGS[model_name]
+    x = O.white_noise(batch, L_SAMPLES, 1234).to(dev)
+    bank = O.sinc_filterbank(cfg["filts"][0], cfg["first_conv"]).to(dev)
+    O.forward(model_name, sd, cfg, x, None, bank)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(repeats):
+        O.forward(model_name, sd, cfg, x, None, bank)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / repeats
+    del sd, x
+    torch.cuda.empty_cache()
+    return batch / (ms * 1e-3), ms
+
+
 def cpu_oracle_throughput(model_name: str, n_utt: int, repeats: int, warmup: int = 1):
     import torch
     from oracle import aasist_oracle as O
@@ -167,17 +204,23 @@ def run_evalset(args, model, dev, world, rank):
     from aasist_b200.scoring import score_utterances
     n_total, chunk = 71237, 512
 
+    from aasist_b200.scoring import shard_bounds
+    lo_r, hi_r, _ = shard_bounds(n_total, world, rank)
+    # the rank's whole shard is generated BEFORE the timed region and stays resident (18.4 GB at N=1)
+    shard = torch.empty(hi_r - lo_r, L_SAMPLES, device=dev)
+    for cid in range(lo_r // chunk, (hi_r - 1) // chunk + 1):
+        g = torch.Generator(device=dev).manual_seed(1234 + cid)
+        xc = 0.05 * torch.randn(chunk, L_SAMPLES, device=dev, generator=g)
+        lo, hi = max(lo_r, cid * chunk), min(hi_r, (cid + 1) * chunk)
+        shard[lo - lo_r:hi - lo_r] = xc[lo - cid * chunk:hi - cid * chunk]
+    del xc
+
     def source(start, stop):
-        parts = []
-        for cid in range(start // chunk, (stop - 1) // chunk + 1):
-            g = torch.Generator(device=dev).manual_seed(1234 + cid)
-            xc = 0.05 * torch.randn(chunk, L_SAMPLES, device=dev, generator=g)
-            lo, hi = max(start, cid * chunk), min(stop, (cid + 1) * chunk)
-            parts.append(xc[lo - cid * chunk:hi - cid * chunk])
-        return torch.cat(parts) if len(parts) > 1 else parts[0]
+        return shard[start - lo_r:stop - lo_r]
 
     with torch.no_grad():
-        score_utterances(model, source, 4 * chunk * world, batch_size=chunk)        # warm-up
+        for _ in range(2):
+            model(shard[:chunk])                                                      # warm-up
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -199,12 +242,21 @@ def run_evalset(args, model, dev, world, rank):
             "data": "synthetic",
             "config": {"workload": f"{args.model} eval-set-sized scoring: {n_total} utterances, L={L_SAMPLES}, contiguous "
                                    f"block shards over {world} GPU(s), local batch {chunk}, one all-gather of scores; "
-                                   "waveform generation on device is inside the timed region",
+                                   "the synthetic shard is generated on the device before the timed region",
                        "n_utterances": n_total, "precision": model.precision},
             "gpu_launches": int(model.launch_count() - launches0),
             "scores_checksum": float(scores.double().sum().item()), "scores_head": scores[:4].tolist()})
     if world > 1:
         dist.destroy_process_group()
+
+
+def _lib_sha16() -> str:
+    import hashlib
+    from aasist_b200 import _lib
+    try:
+        return hashlib.sha256(open(_lib.LIB_PATH, "rb").read()).hexdigest()[:16]
+    except OSError:
+        return ""
 
 
 def run_native(args):
@@ -219,10 +271,6 @@ def run_native(args):
     if args.gpus > 1 and world == 1:
         raise SystemExit("for --gpus N>1 launch with: python -m torch.distributed.run --nnodes=1 "
                          "--nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...")
-    if "AASIST_NCCL_DEBUG" in os.environ:
-        os.environ["NCCL_DEBUG"] = os.environ["AASIST_NCCL_DEBUG"]
-    else:
-        os.environ.pop("NCCL_DEBUG", None)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -236,28 +284,29 @@ def run_native(args):
     model = model.to(dev).eval()
     precision = model.precision
 
+    if args.workload == "evalset":
+        return run_evalset(args, model, dev, world, rank)
+
     # synthetic 4 s waveforms, already resident in HBM for the device-timed region.
     # 512 x 64600 fp32 = 132 MB per GPU > the 126 MB L2, and every intermediate is far larger,
     # so no timed iteration can be served from L2.
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     x = 0.05 * torch.randn(B, L_SAMPLES, device=dev, generator=g)
-    gathered = torch.empty(world * B, device=dev) if world > 1 else None
+    K = args.steps
+    W = max(3, args.warmup)
+    local = torch.empty(K * B, device=dev)                       # this rank's scores of the timed region
+    gathered = torch.empty(world * K * B, device=dev) if world > 1 else None
 
-    if args.workload == "evalset":
-        return run_evalset(args, model, dev, world, rank)
-
-    def step():
-        _, out = model(x)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, out[:, 1].contiguous())
-        return out
+    def run_steps(k):
+        for i in range(k):
+            _, out = model(x)
+            local[i * B:(i + 1) * B] = out[:, 1]
+        if world > 1:                                            # ONE all-gather at the end of the shard
+            dist.all_gather_into_tensor(gathered, local)
 
     with torch.no_grad():
-        for _ in range(max(3, args.warmup)):
-            out = step()
+        run_steps(W)
         torch.cuda.synchronize()
-        model.profile(True)
-        model.profile_report(reset=True)
         launches0 = model.launch_count()
         sampler = ClockSampler(local_rank)
         if rank == 0:
@@ -267,8 +316,7 @@ def run_native(args):
         torch.cuda.synchronize()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-        for _ in range(args.steps):
-            out = step()
+        run_steps(K)
         ev1.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -276,106 +324,150 @@ def run_native(args):
         elapsed_ms = ev0.elapsed_time(ev1)
         clocks = sampler.stop() if rank == 0 else None
         launches = model.launch_count() - launches0
-        prof = model.profile_report(reset=True)
-        model.profile(False)
         t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
 
-        # end to end through the public host-buffer call: pinned host input -> H2D -> forward ->
-        # D2H of (last_hidden, logits), every step (reference main.py:372-377 does the same per batch)
+        # end to end through the public scoring loop with HOST buffers: pinned host batch -> staging -> H2D on the
+        # copy stream -> forward, K times without waiting (the H2D of batch n+1 runs under the forward of batch n),
+        # then ONE wait, the score all-gather (N>1) and the device->host read of the scores
+        # (replaces reference main.py:364-378, which round-trips every batch)
         e2e = None
         if not args.no_e2e:
             xh = x.cpu().pin_memory()
-            model.score_host(xh)
+            host_scores = torch.empty(world * K * B).pin_memory()
+
+            def run_e2e(k):
+                model.score_begin(K * B, B, L_SAMPLES, dev)      # same capacity in the warm-up: no allocation when timed
+                for _ in range(k):
+                    model.score_submit(xh)
+                out = model.score_finish(on_device=True)
+                sc = out[:, 1].contiguous()
+                if world > 1:
+                    dist.all_gather_into_tensor(gathered[:world * k * B], sc)
+                    sc = gathered[:world * k * B]
+                host_scores[:sc.numel()].copy_(sc, non_blocking=True)
+
+            run_e2e(2)
+            torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            n_e2e = max(2, min(args.steps, 5))
             e0.record()
-            for _ in range(n_e2e):
-                lh_h, out_h = model.score_host(xh)
-                if world > 1:
-                    dist.all_gather_into_tensor(gathered, out_h[:, 1].to(dev, non_blocking=True))
+            run_e2e(K)
             e1.record()
             torch.cuda.synchronize()
             te = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
             if world > 1:
                 dist.all_reduce(te, op=dist.ReduceOp.MAX)
-            e2e = {"value": world * B * n_e2e / (float(te.item()) * 1e-3), "unit": "utt/s",
-                   "h2d_bytes_per_step": B * L_SAMPLES * 4, "d2h_bytes_per_step": B * (model.hidden_dim + 2) * 4,
-                   "steps": n_e2e}
+            e2e = {"value": world * B * K / (float(te.item()) * 1e-3), "unit": "utt/s",
+                   "h2d_bytes_per_step": B * L_SAMPLES * 4, "d2h_bytes_per_step": world * B * 4,
+                   "steps": K, "ms_per_step": float(te.item()) / K,
+                   "api": "aasist_b200.Model.score_begin/score_submit/score_finish (C ABI aasist_score_*), pinned host "
+                          "input, scores read back to the host once at the end of the timed region"}
+
+        # UNTIMED pass with per-launch CUDA events (on the launching stream) for the per-kernel table
+        n_prof = max(2, min(K, 5))
+        model.profile(True)
+        model.profile_report(reset=True)
+        for _ in range(n_prof):
+            model(x)
+        prof = model.profile_report(reset=True)
+        model.profile(False)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    value = world * B * args.steps / (elapsed_ms * 1e-3)
+    value = world * B * K / (elapsed_ms * 1e-3)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    # roofline of the dominant kernel (largest share of the timed region, CUDA events per launch)
+    # roofline of the dominant kernel (largest share of the profiled pass, CUDA events per launch)
     prof.sort(key=lambda r: -r["ms"])
     total_kernel_ms = sum(r["ms"] for r in prof) or 1.0
     top = prof[0] if prof else None
     roofline = None
+    from aasist_b200 import workmodel
     if top is not None:
-        from aasist_b200 import workmodel
         flops_step = workmodel.kernel_flops(name, top["kernel"], B, L_SAMPLES)   # algorithmic FLOPs / step
-        n_launch = max(1, top["launches"] // args.steps)                          # launches of it per step
+        n_launch = max(1, top["launches"] // n_prof)                              # launches of it per step
         avg_launch_ms = top["ms"] / max(1, top["launches"])
         peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
         peak_src = ("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks
                     else "fallback 1.4 PF sustained (B200_PROFILING.md)")
         ach = (flops_step / n_launch) / (avg_launch_ms * 1e-3) / 1e12
-        traffic = None
+        # ncu DRAM bytes of this kernel: only from a capture of THIS build (the table records the library hash)
+        traffic, traffic_src = None, None
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["bytes_per_utterance"]
-            if name == "AASIST" and top["kernel"] in tr:
-                traffic = int(tr[top["kernel"]] * (B / n_launch))       # ncu DRAM bytes per launch
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            per_utt = tr.get("bytes_per_utterance", {}).get(name, {})
+            if tr.get("lib_sha16") == _lib_sha16() and top["kernel"] in per_utt:
+                traffic = int(per_utt[top["kernel"]] * (B / n_launch))
+                traffic_src = tr.get("source")
+            elif top["kernel"] in per_utt:
+                traffic_src = "stale: profiles/ncu_traffic.json was captured on another build (%s)" % tr.get("lib_sha16")
         except Exception:
             pass
+        executed = 3.0 if precision == "f16x3" else 1.0
         roofline = {"bound": "tensor", "kernel": top["kernel"], "achieved": ach, "peak": peak_tf,
-                    "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
-                    "executed_tflops": 3.0 * ach if precision == "f16x3" else ach,
-                    "executed_frac": (3.0 * ach if precision == "f16x3" else ach) / peak_tf,
+                    "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
+                    "executed_tflops": executed * ach, "executed_frac": executed * ach / peak_tf,
                     "peak_source": peak_src, "share_of_step": top["ms"] / total_kernel_ms,
                     "flops_per_launch": flops_step / n_launch, "launches_per_step": n_launch,
                     "avg_launch_ms": avg_launch_ms,
                     "note": "achieved = ALGORITHMIC FLOPs per launch (2xMAC of the reference fp32 ops, "
-                            "aasist_b200/workmodel.py) / mean CUDA-event launch time; the f16x3 path executes 3 "
-                            "tcgen05 MMAs per reference MAC, so tensor-pipe work is 3x this figure (executed_tflops / "
-                            "executed_frac); traffic = ncu dram bytes per launch (profiles/ncu_traffic.json)"}
-    from aasist_b200 import workmodel
+                            "aasist_b200/workmodel.py) / mean CUDA-event launch time, measured in a separate untimed "
+                            "pass; the f16x3 path executes 3 tcgen05 MMAs per reference MAC, so tensor-pipe work is 3x "
+                            "this figure (executed_tflops / executed_frac)"}
     line = {
         "metric": "AASIST utterances/sec (4 s, 64600 samples)", "value": value, "unit": "utt/s",
-        "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32" if precision == "fp32" else "f16x3(split)+f32acc",
         "data": "synthetic",
         "config": {"workload": f"{name} (config/{name}.conf, shipped {name}.pth) eval scoring forward, "
                                f"batch {B} per GPU, L={L_SAMPLES}",
                    "model_name": name, "batch_per_gpu": B, "global_batch": B * world, "samples": L_SAMPLES,
-                   "precision": precision, "parallelism": f"utterance-sharded dp{world}, one NCCL all-gather of scores per step",
+                   "precision": precision,
+                   "parallelism": f"utterance-sharded dp{world}, one NCCL all-gather of the scores at the end of the "
+                                  "timed region",
                    "l2_policy": "inputs (132 MB/GPU) and every intermediate exceed the 126 MB L2"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "roofline": roofline,
-        "kernels": [{"kernel": r["kernel"], "launches": r["launches"], "ms_per_step": r["ms"] / args.steps,
+        "kernels": [{"kernel": r["kernel"], "launches": r["launches"], "ms_per_step": r["ms"] / n_prof,
                      "share": r["ms"] / total_kernel_ms} for r in prof],
+        "kernels_note": f"per-launch CUDA events from a separate untimed pass of {n_prof} steps",
         "algorithmic_tflops": value * (FLOPS_PER_UTT[name] if L_SAMPLES == 64600 else
                                        2.0 * sum(workmodel.stage_macs(name, L_SAMPLES).values())) / 1e12,
+        "lib_sha16": _lib_sha16(),
     }
+    if not args.no_eager_baseline:
+        try:
+            rate, ms = gpu_eager_throughput(name, dev)
+            line["gpu_eager_baseline"] = {
+                "value": rate, "unit": "utt/s", "batch": 64, "ms_per_batch": ms,
+                "what": "oracle/aasist_oracle.py forward executed eagerly by torch on this GPU, fp32, TF32 disabled "
+                        "(cuDNN/cuBLAS): the reference's own deployment (main.py requires CUDA), batch 64"}
+        except Exception as e:                                    # never lose the line over a baseline
+            line["gpu_eager_baseline"] = {"error": str(e)[:200]}
     if not args.no_cpu_baseline and world >= 1:
         n_cpu = 8
         best, mean, cores, times = cpu_oracle_throughput(name, n_cpu, 2, warmup=1)
         line["cpu_baseline"] = {"value": best, "unit": "utt/s", "cores": cores, "kind": "port",
                                 "sample": f"{n_cpu} utterances, best of 2 after 1 warm-up, torch CPU fp32, "
                                           f"{cores} threads (oracle/aasist_oracle.py)"}
+        if L_SAMPLES == 64600:
+            # BASELINE.json configs[0] / BASELINE.md section 3 (C1): AASIST-L forward on CPU, batch 24
+            b1, m1, cores, _ = cpu_oracle_throughput("AASIST-L", 24, 2, warmup=1)
+            line["cpu_baseline"]["c1_aasist_l_batch24"] = {
+                "value": b1, "unit": "utt/s", "cores": cores,
+                "sample": "AASIST-L, batch 24, L=64600, best of 2 after 1 warm-up (BASELINE configs[0])"}
     _emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define AASIST_B200_ABI_VERSION 1
+#define AASIST_B200_ABI_VERSION 2
 
 enum {
   AASIST_OK = 0,
@@ -40,7 +40,19 @@ enum {
 enum {
   AASIST_KIND_AASIST = 0,   /* models/AASIST.py:728-921 with the (2,3) Residual_block encoder
                                (models/RawNetGatSpoofST.py:225-278) the shipped weights fit   */
-  AASIST_KIND_RAWGAT_ST = 1 /* models/RawNetGatSpoofST.py:281-356                            */
+  AASIST_KIND_RAWGAT_ST = 1,/* models/RawNetGatSpoofST.py:281-356                            */
+  AASIST_KIND_ROBUST = 2    /* models/AASIST_Robust.py:90-303 (eval): `first_conv` sinc filters of 1025 taps at
+                               stride 256 (:96-102), the fork's 3x3 Residual_block encoder, one heterogeneous
+                               branch, auxiliary head on the mean encoder feature, softmax-weighted ensemble */
+};
+
+/* encoder block type (AASIST / ROBUST kinds) */
+enum {
+  AASIST_ENC_RESIDUAL23 = 0, /* (2,3) Residual_block, models/RawNetGatSpoofST.py:225-278: what the shipped
+                                checkpoints hold (tensor-core path available)                          */
+  AASIST_ENC_RES2NET = 1,    /* Res2NetBlock + SELayer, models/AASIST.py:506-669: what the fork's
+                                `Model(d_args)` builds (fp32 CUDA-core kernels)                        */
+  AASIST_ENC_RESIDUAL33 = 2  /* the fork's 3x3 Residual_block, models/AASIST.py:672-725 (AASIST-Robust) */
 };
 
 /* arithmetic of the sinc / encoder convolutions (graph stages are always fp32) */
@@ -62,8 +74,24 @@ typedef struct aasist_config {
   double pool_ratios[4];     /* d_args["pool_ratios"]         (AASIST kind only)             */
   double temperatures[4];    /* d_args["temperatures"]        (AASIST kind only)             */
   int32_t sample_rate;       /* 16000 (CONV.__init__ default, AASIST.py:430)                 */
-  int32_t reserved[7];
+  int32_t encoder;           /* AASIST_ENC_* (ROBUST kind: must be RESIDUAL33)               */
+  int32_t res2net_width;     /* d_args.get("res2net_width", 14)   (AASIST.py:739)            */
+  int32_t res2net_scale;     /* d_args.get("res2net_scale", 8)    (AASIST.py:740)            */
+  int32_t spk_emb_dim;       /* d_args["spk_emb_dim"] when d_args["speaker_conditioning"], else 0
+                                (SpeakerConditioningModule on gat_dims[1], AASIST.py:743-755) */
+  int32_t spk_level;         /* 0 = "frame", 1 = "utterance" (AASIST.py:746)                 */
+  int32_t spk_use_attention; /* d_args.get("use_attention", True) (AASIST.py:747)            */
+  int32_t reserved[1];
 } aasist_config;
+
+/* Per-call options of `Model.forward(x, Freq_aug=..., speaker_embedding=...)` (AASIST.py:806). */
+typedef struct aasist_forward_opts {
+  const float* speaker_embedding; /* DEVICE (B, spk_emb_dim) fp32, or NULL (reference main.py:375 passes None) */
+  int32_t freq_mask_start;        /* Freq_aug (AASIST.py:486-490): rows [start, start+count) of the sinc bank   */
+  int32_t freq_mask_count;        /* are zeroed for this call; count 0 = no masking.  The CALLER draws A, A0    */
+                                  /* (the reference uses numpy's and Python's global RNGs)                      */
+  int32_t reserved[4];
+} aasist_forward_opts;
 
 typedef struct aasist_handle aasist_handle;
 
@@ -114,6 +142,15 @@ int aasist_forward(aasist_handle* h, const float* x, int32_t B, int32_t L,
                    float* last_hidden, float* logits, int32_t* topk_idx, float* pool_scores,
                    void* workspace, int64_t workspace_bytes, void* stream);
 
+/* `Model.forward(x, Freq_aug, speaker_embedding)` with its optional arguments; `opts` may be NULL
+ * (= aasist_forward).  For AASIST_KIND_ROBUST `last_hidden` receives the (B,2) ensemble logits and
+ * `logits` the main head's logits -- the reference returns `(ensemble_logits, logits)`
+ * (AASIST_Robust.py:303).  `workspace` may be NULL: the handle then uses (and grows on demand) a
+ * scratch buffer of its own, shared with aasist_forward_host and the scoring stream. */
+int aasist_forward_ex(aasist_handle* h, const float* x, int32_t B, int32_t L, const aasist_forward_opts* opts,
+                      float* last_hidden, float* logits, int32_t* topk_idx, float* pool_scores,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Same call with HOST buffers: pinned staging + H2D of x, forward, D2H of logits and
  * last_hidden (either may be NULL), stream-synchronised before return.  This is what
  * reference main.py:372-377 does per batch (`.to(device)` ... `.cpu()`). */
@@ -128,6 +165,40 @@ int aasist_forward_host(aasist_handle* h, const float* x_host, int32_t B, int32_
  * length (>= 1; an empty utterance is an error like the reference's ZeroDivisionError). */
 int aasist_pad_batch(aasist_handle* h, const float* samples_dev, const int64_t* offsets_host,
                      const int32_t* lengths_host, int32_t B, int32_t max_len, float* out_dev, void* stream);
+
+/* Generalisation used by the other staging functions of data_utils.py: row b of the (B, row_len) output is
+ *   out[b][i] = i < target_b ? x_b[(start_b + i) mod len_b] : 0
+ * `starts_host` NULL = all 0; `targets_host` NULL = row_len for every row.  With the reference's random draws made
+ * by the caller this reproduces, bit-exactly,
+ *   pad               (data_utils.py:45-52)    start 0, target = row_len = max_len
+ *   pad_random        (data_utils.py:55-65)    start = np.random.randint(len - max_len) when len >= max_len
+ *   dynamic_chunk_size(data_utils.py:68-97)    target = randint(min, max+1), start = randint(0, len-target+1)
+ *   pad_sequence      (data_utils.py:100-119)  start 0, target = min(len, row_len), row_len = the batch maximum
+ *                                              rounded up to a multiple of 4 (aasist_pad_sequence_length) */
+int aasist_stage_batch(aasist_handle* h, const float* samples_dev, const int64_t* offsets_host,
+                       const int32_t* lengths_host, const int32_t* starts_host, const int32_t* targets_host,
+                       int32_t B, int32_t row_len, float* out_dev, void* stream);
+/* ((max(lengths) + 3) / 4) * 4  (data_utils.py:108-110) */
+int32_t aasist_pad_sequence_length(const int32_t* lengths_host, int32_t B);
+
+/* ---- the scoring loop (the caller of the path) --------------------------------------------------- */
+/* Replaces the per-batch `batch_x.to(device)` -> `model(batch_x)` -> `batch_out[:,1].cpu()` round trip of
+ * produce_evaluation_file (main.py:364-378) with a pipeline: `aasist_score_submit` copies one batch of HOST
+ * utterances through one of two pinned staging buffers, issues its H2D on a copy stream and enqueues its forward
+ * behind it -- the H2D of batch n+1 runs under the forward of batch n, and the call returns without waiting for
+ * either.  Scores (logits, and last_hidden when requested) accumulate in device memory;
+ * `aasist_score_finish` waits once and copies them to the host.  One scratch buffer serves every forward.
+ *   begin : capacity = total utterances of the session; max_batch = largest B of any submit; L = samples each
+ *   submit: x_host (B, L) fp32, pageable or pinned; returns after the staging copy (no device wait unless both
+ *           staging buffers are still in flight)
+ *   finish: logits_out (n, 2) and last_hidden_out (n, hidden_dim) may each be NULL and may be HOST or DEVICE
+ *           pointers (a multi-GPU caller all-gathers the device copy without a host round trip); `logits_dev_out`,
+ *           when not NULL, receives the device pointer of the accumulated logits (valid until the next begin /
+ *           destroy).  Waits for the stream once.  Returns n, the number of utterances scored. */
+int aasist_score_begin(aasist_handle* h, int64_t capacity, int32_t max_batch, int32_t L, void* stream);
+int aasist_score_submit(aasist_handle* h, const float* x_host, int32_t B);
+int64_t aasist_score_finish(aasist_handle* h, float* logits_out, float* last_hidden_out,
+                            const float** logits_dev_out);
 
 /* ---- detection metrics (the step after the path) ---------------------------------------------- */
 /* Replaces compute_det_curve / compute_eer (evaluation.py:120-154) and the t-DCF curve of compute_tDCF

@@ -14,7 +14,7 @@ DEV = torch.device("cuda:0")
 
 @functools.lru_cache(maxsize=None)
 def native_model(name: str, precision: str = "fp32"):
-    cls = aasist_b200.RawGATSTModel if name == "RawGAT-ST" else aasist_b200.Model
+    cls = {"RawGAT-ST": aasist_b200.RawGATSTModel, "AASIST-Robust": aasist_b200.RobustModel}.get(name, aasist_b200.Model)
     m = cls(aasist_b200.CONFIGS[name], precision=precision)
     m.load_state_dict(load_sd(name), strict=True)
     m = m.to(DEV).eval()
@@ -41,12 +41,22 @@ def stage_frontend(m, x):
     return out
 
 
+def stage_frontend_raw(m, x, shape):
+    """aasist_frontend for models whose front-end geometry differs (AASIST-Robust): `shape` = expected output."""
+    lib = _lib.load()
+    B, L = x.shape
+    out = torch.empty(*shape, device=DEV)
+    _lib.check(lib.aasist_frontend(m._handle, x.data_ptr(), B, L, out.data_ptr(), None, 0, None))
+    torch.cuda.synchronize()
+    return out
+
+
 def stage_block(m, enc, index, x_in, co):
     lib = _lib.load()
     x_in = x_in.contiguous()
     B, ci, H, W = x_in.shape
     out = torch.empty(B, co, 23, W // 3, device=DEV)
-    nbytes = 4 * B * max(co, ci, 32) * 24 * W * 4 + (1 << 20)
+    nbytes = 4 * B * (2 * max(ci, 1) + max(co, ci, 32)) * 24 * W * 4 + (1 << 22)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
     _lib.check(lib.aasist_encoder_block(m._handle, enc, index, x_in.data_ptr(), B, W, out.data_ptr(),
                                         ws.data_ptr(), nbytes, None))

@@ -10,7 +10,9 @@ from oracle import aasist_oracle as O
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
 WDIR = os.path.join(ROOT, "aasist_b200", "weights")
-WEIGHTS = {"AASIST": "AASIST.pth", "AASIST-L": "AASIST-L.pth", "RawGAT-ST": "RawGATST_seed1234.pth"}
+WEIGHTS = {"AASIST": "AASIST.pth", "AASIST-L": "AASIST-L.pth", "RawGAT-ST": "RawGATST_seed1234.pth",
+           "AASIST2": "AASIST2_seed1234.pth", "AASIST2-small": "AASIST2-small_seed1234.pth",
+           "AASIST-Robust": "AASIST-Robust_seed1234.pth"}
 GENERATORS = {"white": O.white_noise, "speech": O.speech_like,
               "speech16k": O.speech_like, "speech96k": O.speech_like, "speech128k": O.speech_like,
               "speech192k": O.speech_like, "speech256k": O.speech_like}
