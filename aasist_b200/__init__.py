@@ -7,7 +7,7 @@ from .model import Model, RawGATSTModel, RobustModel
 from .scoring import get_model, score_utterances, write_score_file
 
 # precisions whose kernels are built into libaasist_b200.so
-BUILT_PRECISIONS = ("fp32", "f16x3")
+BUILT_PRECISIONS = ("fp32", "f16x3")      # smoke()/default set; "f16x2" is the opt-in reduced-product mode
 
 __all__ = ["BUILT_PRECISIONS", "CONFIGS", "WEIGHTS", "Model", "RawGATSTModel", "RobustModel", "get_model", "load_model_config",
            "score_utterances", "weights_path", "write_score_file"]

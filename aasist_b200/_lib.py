@@ -15,8 +15,8 @@ LIB_PATH = os.environ.get("AASIST_B200_LIB") or os.path.join(_HERE, "csrc", "lib
 KIND_AASIST, KIND_RAWGAT_ST, KIND_ROBUST = 0, 1, 2
 ENC_RESIDUAL23, ENC_RES2NET, ENC_RESIDUAL33 = 0, 1, 2
 ABI_VERSION = 2
-PREC_FP32, PREC_F16X3 = 0, 1
-PRECISIONS = {"fp32": PREC_FP32, "f16x3": PREC_F16X3}
+PREC_FP32, PREC_F16X3, PREC_F16X2 = 0, 1, 2
+PRECISIONS = {"fp32": PREC_FP32, "f16x3": PREC_F16X3, "f16x2": PREC_F16X2}
 
 
 class AasistConfig(C.Structure):

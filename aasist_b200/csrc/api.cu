@@ -669,12 +669,12 @@ constexpr int kChunkF32 = 32;  // utterances per encoder pass on the fp32 path (
 
 // does the whole encoder run on the tensor-core path?
 static inline bool tc_encoder(const aasist_handle* h) {
-  return h->cfg.precision == AASIST_PREC_F16X3 && h->cfg.encoder == AASIST_ENC_RESIDUAL23 &&
+  return h->cfg.precision != AASIST_PREC_FP32 && h->cfg.encoder == AASIST_ENC_RESIDUAL23 &&
          h->cfg.kind != AASIST_KIND_ROBUST;
 }
 // tensor-core sinc front end feeding fp32 encoder kernels (Res2Net encoder with precision f16x3)
 static inline bool tc_frontend_only(const aasist_handle* h) {
-  return h->cfg.precision == AASIST_PREC_F16X3 && h->cfg.encoder != AASIST_ENC_RESIDUAL23 &&
+  return h->cfg.precision != AASIST_PREC_FP32 && h->cfg.encoder != AASIST_ENC_RESIDUAL23 &&
          h->cfg.kind != AASIST_KIND_ROBUST;
 }
 
@@ -721,7 +721,8 @@ int aasist_create(const aasist_config* cfg, aasist_handle** out) {
     set_error("unknown model kind %d", cfg->kind);
     return AASIST_E_INVALID;
   }
-  if (cfg->precision != AASIST_PREC_FP32 && cfg->precision != AASIST_PREC_F16X3) {
+  if (cfg->precision != AASIST_PREC_FP32 && cfg->precision != AASIST_PREC_F16X3 &&
+      cfg->precision != AASIST_PREC_F16X2) {
     set_error("unknown precision mode %d", cfg->precision);
     return AASIST_E_INVALID;
   }
@@ -922,7 +923,7 @@ static int finalize_impl(aasist_handle* h) {
       if (rc) return rc;
     }
   if ((rc = pack_graph(h))) return rc;
-  if (h->cfg.precision == AASIST_PREC_F16X3 && h->cfg.kind != AASIST_KIND_ROBUST)
+  if (h->cfg.precision != AASIST_PREC_FP32 && h->cfg.kind != AASIST_KIND_ROBUST)
     if ((rc = tc_finalize(h))) return rc;
   h->finalized = true;
   return AASIST_OK;
@@ -1342,7 +1343,7 @@ int aasist_frontend(aasist_handle* h, const float* x, int32_t B, int32_t L, floa
   (void)workspace;
   (void)workspace_bytes;
   if (h->cfg.kind == AASIST_KIND_ROBUST) return launch_frontend_strided_f32(h, x, B, L, out, 0, 0, (cudaStream_t)stream);
-  if (h->cfg.precision == AASIST_PREC_F16X3) return tc_frontend_to_f32(h, x, B, L, out, 0, 0, (cudaStream_t)stream);
+  if (h->cfg.precision != AASIST_PREC_FP32) return tc_frontend_to_f32(h, x, B, L, out, 0, 0, (cudaStream_t)stream);
   return launch_frontend_f32(h, x, B, L, out, 0, 0, (cudaStream_t)stream);
 }
 

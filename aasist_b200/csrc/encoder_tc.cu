@@ -66,6 +66,7 @@ struct ConvTcParams {
   const uint8_t* wimg;     // pre-swizzled weight image (shared-memory layout)
   int wimg_bytes;
   long long* stats;        // optional: MMA-warp wait cycles per CTA [total, full(TMA), tempty(epilogue)]
+  int products;            // 3 = a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (f16x3); 2 = without the weight correction (f16x2)
 };
 
 struct ConvTc {            // one convolution's packed device state
@@ -323,7 +324,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (kc < nkc) {
           umma_f16(d_tmem, a_hi + 2 * kc, w_hi + 2 * kc, idesc, (kc > 0 || !fresh) ? 1u : 0u);
           umma_f16(d_tmem, a_lo + 2 * kc, w_hi + 2 * kc, idesc, 1);
-          umma_f16(d_tmem, a_hi + 2 * kc, w_lo + 2 * kc, idesc, 1);
+          if (p.products == 3) umma_f16(d_tmem, a_hi + 2 * kc, w_lo + 2 * kc, idesc, 1);
         }
       }
     };
@@ -871,6 +872,7 @@ static int launch_conv(aasist_handle* h, const char* name, const CUtensorMap& tm
   want_stats = 0;   // the instrumentation is compiled in only by tools/variant_build.sh -DAASIST_KERNEL_STATS
 #endif
   p.stats = nullptr;
+  p.products = h->cfg.precision == AASIST_PREC_F16X2 ? 2 : 3;
   if (want_stats) {
     AASIST_CUDA(cudaMalloc(&p.stats, sizeof(long long) * 4 * grid));
     AASIST_CUDA(cudaMemset(p.stats, 0, sizeof(long long) * 4 * grid));

@@ -46,7 +46,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=512)
     ap.add_argument("--samples", type=int, default=64600,
                     help="utterance length (SURVEY 8(d) C5 length sweep; the headline metric is quoted at 64600)")
-    ap.add_argument("--precision", default=None, help="fp32 | f16x3 (default: package default)")
+    ap.add_argument("--precision", default=None,
+                    help="fp32 | f16x3 (default) | f16x2 (opt-in reduced-product mode; its error against the reference "
+                         "goldens is measured and printed in the line)")
     ap.add_argument("--workload", default="batch", choices=["batch", "evalset"],
                     help="batch: BASELINE configs[1] (default, the contract line); evalset: configs[2], one pass over "
                          "71,237 synthetic utterances sharded across the ranks with one score all-gather")
@@ -250,6 +252,40 @@ def run_evalset(args, model, dev, world, rank):
         dist.destroy_process_group()
 
 
+def golden_parity(model, name: str, dev):
+    """Error of `model` against the committed reference goldens (tests/golden/<name>_speech*.npz: logits and ordered
+    GraphPool indices produced by the unmodified reference): max |logit error| and the fraction of utterances whose
+    ordered top-k indices all equal the reference's.  Reported for any non-default precision mode."""
+    import glob
+    import numpy as np
+    import torch
+    sys.path.insert(0, ROOT)
+    from tests.util import golden_input, load_golden, pools_of
+    worst, n_utt, n_ok, n_pos, n_pos_ok = 0.0, 0, 0, 0, 0
+    model.record_topk = True
+    try:
+        for path in sorted(glob.glob(os.path.join(ROOT, "tests", "golden", f"{name}_speech*.npz"))):
+            tag = os.path.basename(path)[len(name) + 1:-4]
+            gold, meta = load_golden(name, tag)
+            x = golden_input(meta).to(dev)
+            _, out = model(x)
+            torch.cuda.synchronize()
+            worst = max(worst, float(np.abs(out.cpu().numpy() - gold["output"]).max()))
+            ref = np.concatenate([gold[p + ".idx"] for p in pools_of(name)], axis=1)
+            got = model.last_topk.cpu().numpy()
+            same = got == ref
+            n_utt += same.shape[0]
+            n_ok += int(same.all(axis=1).sum())
+            n_pos += same.size
+            n_pos_ok += int(same.sum())
+    finally:
+        model.record_topk = False
+    return {"logits_max_abs_err": worst, "utterances": n_utt, "ordered_topk_match_rate": n_ok / max(1, n_utt),
+            "topk_positions": n_pos, "topk_positions_equal": n_pos_ok,
+            "fixtures": f"tests/golden/{name}_speech*.npz (reference-generated)",
+            "ships": bool(worst <= 1e-3 and n_ok == n_utt)}
+
+
 def _lib_sha16() -> str:
     import hashlib
     from aasist_b200 import _lib
@@ -414,7 +450,9 @@ def run_native(args):
                 traffic_src = "stale: profiles/ncu_traffic.json was captured on another build (%s)" % tr.get("lib_sha16")
         except Exception:
             pass
-        executed = 3.0 if precision == "f16x3" else 1.0
+        # tensor-pipe products per reference MAC: 3 everywhere in f16x3; f16x2 keeps 3 in the sinc stage and block 0
+        executed = 1.0 if precision == "fp32" else (
+            2.0 if precision == "f16x2" and not top["kernel"].startswith(("enc0", "sinc")) else 3.0)
         roofline = {"bound": "tensor", "kernel": top["kernel"], "achieved": ach, "peak": peak_tf,
                     "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
                     "executed_tflops": executed * ach, "executed_frac": executed * ach / peak_tf,
@@ -423,13 +461,13 @@ def run_native(args):
                     "avg_launch_ms": avg_launch_ms,
                     "note": "achieved = ALGORITHMIC FLOPs per launch (2xMAC of the reference fp32 ops, "
                             "aasist_b200/workmodel.py) / mean CUDA-event launch time, measured in a separate untimed "
-                            "pass; the f16x3 path executes 3 tcgen05 MMAs per reference MAC, so tensor-pipe work is 3x "
-                            "this figure (executed_tflops / executed_frac)"}
+                            "pass; the f16x3 path executes 3 tcgen05 MMAs per reference MAC (f16x2: 2 in blocks "
+                            "1-5), so tensor-pipe work is that multiple of this figure (executed_tflops / executed_frac)"}
     line = {
         "metric": "AASIST utterances/sec (4 s, 64600 samples)", "value": value, "unit": "utt/s",
         "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32" if precision == "fp32" else "f16x3(split)+f32acc",
+        "vs_baseline": None, "dtype": "f32" if precision == "fp32" else f"{precision}(split)+f32acc",
         "data": "synthetic",
         "config": {"workload": f"{name} (config/{name}.conf, shipped {name}.pth) eval scoring forward, "
                                f"batch {B} per GPU, L={L_SAMPLES}",
@@ -447,6 +485,8 @@ def run_native(args):
                                        2.0 * sum(workmodel.stage_macs(name, L_SAMPLES).values())) / 1e12,
         "lib_sha16": _lib_sha16(),
     }
+    if precision != aasist_b200.model.DEFAULT_PRECISION and name in ("AASIST", "AASIST-L"):
+        line["parity_vs_reference_goldens"] = golden_parity(model, name, dev)
     if not args.no_eager_baseline:
         try:
             rate, ms = gpu_eager_throughput(name, dev)

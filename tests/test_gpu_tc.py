@@ -185,3 +185,37 @@ def test_tc_path_agrees_with_fp32_path_on_odd_shapes(B, L):
     herr = (h16 - h32).abs().max().item()
     print(json.dumps({"B": B, "L": L, "logit_err": err, "hidden_err": herr}))
     assert err <= TC_LOGIT_TOL and herr <= TC_LOGIT_TOL, (err, herr)
+
+
+@pytest.mark.parametrize("name", ["AASIST", "AASIST-L"])
+def test_f16x2_reduced_product_mode_error_is_measured(name):
+    """Opt-in precision "f16x2" (two products in encoder blocks 1-5: weights rounded to fp16).
+    Shipping bar for a reduced mode: logits <= 1e-3 AND 100 % ordered-index match on the reference goldens.
+    MEASURED RESULT: neither model holds it (AASIST: 1.0e-3 on the 4 s speech golden and index flips on the long
+    utterances; AASIST-L: top-k flips -- the CPU emulation in tools/precision_emulation.py predicts the same), so
+    the mode is NOT shipped as a default anywhere: it stays an explicitly requested experiment whose error is
+    printed here and in the bench line.  The test pins the measured order of magnitude (a regression guard)."""
+    g = _g()
+    m = g.native_model(name, "f16x2")
+    worst, bad, total, report = 0.0, 0, 0, {}
+    for tag in ("speech", "speech16k", "speech96k", "white"):
+        gold, meta = load_golden(name, tag)
+        x = golden_input(meta).to(g.DEV)
+        m.record_topk = True
+        try:
+            lh, out = m(x)
+            torch.cuda.synchronize()
+            pools = g.split_pools(m.last_topk, m.last_pool_weights, m.topk_layout(meta["L"]))
+        finally:
+            m.record_topk = False
+        err = float(np.abs(out.cpu().numpy() - gold["output"]).max())
+        rep = g.check_pools(pools, gold, pools_of(name))
+        strict = sum(r["strict_mismatch"] for r in rep.values())
+        report[tag] = {"logit_err": err, "strict_topk_mismatch": strict}
+        if tag != "white":                       # white noise has exact/near ties by construction (SURVEY 0.5)
+            worst, bad, total = max(worst, err), bad + strict, total + sum(r["positions"] for r in rep.values())
+    print(json.dumps({"mode": "f16x2", "model": name, "worst_logit_err_speech": worst,
+                      "strict_topk_mismatch_speech": bad, "positions": total, "cases": report}))
+    assert all(np.isfinite(v["logit_err"]) for v in report.values())
+    if name == "AASIST":
+        assert worst <= 3e-3, report             # same order as single-pass TF32 (SURVEY B.2), 20-60x the f16x3 error
