@@ -5,9 +5,30 @@ from __future__ import annotations
 from .configs import CONFIGS
 
 
+def res2net_stage_macs(name: str, length: int = 64600):
+    """MACs per utterance of the fork's Res2Net+SE model (AASIST.py:603-669): split convs, conv_cat, downsample."""
+    from .model import res2net_splits
+    cfg = CONFIGS[name]
+    f = cfg["filts"]
+    taps = cfg["first_conv"] + 1 if cfg["first_conv"] % 2 == 0 else cfg["first_conv"]
+    t = length - taps + 1
+    out = {"sinc": f[0] * taps * t}
+    w = t // 3
+    for i, (ci, co) in enumerate([f[1], f[2], f[3], f[4], f[4], f[4]]):
+        sizes, _ = res2net_splits((ci, co), cfg.get("res2net_width", 14), cfg.get("res2net_scale", 8))
+        out[f"enc{i}.splits"] = sum(n * n * 9 for n in sizes) * 23 * w
+        out[f"enc{i}.conv_cat"] = co * ci * 9 * 23 * w
+        out[f"enc{i}.ds"] = co * ci * 3 * 23 * w if ci != co else 0
+        w //= 3
+    out["graph"] = 11.6e6
+    return out
+
+
 def stage_macs(name: str, length: int = 64600):
     """MACs per utterance by stage: {'sinc', 'enc{i}.conv1', 'enc{i}.conv2', 'enc{i}.ds', 'graph'}."""
     cfg = CONFIGS[name]
+    if "res2net_width" in cfg:
+        return res2net_stage_macs(name, length)
     f = cfg["filts"]
     taps = cfg["first_conv"] + 1 if cfg["first_conv"] % 2 == 0 else cfg["first_conv"]
     t = length - taps + 1
@@ -36,6 +57,12 @@ def kernel_flops(name: str, kernel: str, batch: int, length: int = 64600) -> flo
         return 2.0 * macs * batch
     if kernel.startswith("sinc_frontend"):
         macs = m["sinc"]
+    elif kernel.startswith("res2_conv_cat"):
+        macs = sum(v for k, v in m.items() if k.endswith(".conv_cat"))
+    elif kernel.startswith("res2_split"):
+        macs = sum(v for k, v in m.items() if k.endswith(".splits"))
+    elif kernel.startswith("res2_gate"):
+        macs = sum(v for k, v in m.items() if k.endswith(".ds"))
     elif kernel.startswith("conv1") and "[1->C]" in kernel:
         macs = m["enc0.conv1"]
     elif kernel.startswith("conv1"):

@@ -42,7 +42,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--model", default="AASIST", choices=["AASIST", "AASIST-L", "RawGAT-ST"])
+    ap.add_argument("--model", default="AASIST", choices=["AASIST", "AASIST-L", "RawGAT-ST", "AASIST2"],
+                    help="AASIST2 = the fork's Res2Net+SE model (config/AASIST2.conf; seeded weights, no checkpoint exists)")
     ap.add_argument("--batch", type=int, default=512)
     ap.add_argument("--samples", type=int, default=64600,
                     help="utterance length (SURVEY 8(d) C5 length sweep; the headline metric is quoted at 64600)")
@@ -73,21 +74,32 @@ def gpu_eager_throughput(model_name: str, dev, batch: int = 64, repeats: int = 3
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     sd = {k: v.to(dev) for k, v in torch.load(aasist_b200.weights_path(model_name), map_location="cpu").items()}
-    cfg = O.CONFIGS[model_name]
+    cfg, fwd = _oracle_forward(model_name)
     x = O.white_noise(batch, L_SAMPLES, 1234).to(dev)
     bank = O.sinc_filterbank(cfg["filts"][0], cfg["first_conv"]).to(dev)
-    O.forward(model_name, sd, cfg, x, None, bank)
+    fwd(sd, x, bank)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(repeats):
-        O.forward(model_name, sd, cfg, x, None, bank)
+        fwd(sd, x, bank)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / repeats
     del sd, x
     torch.cuda.empty_cache()
     return batch / (ms * 1e-3), ms
+
+
+def _oracle_forward(model_name: str):
+    """(config, forward(sd, x, bank)) of the CPU/GPU-eager oracle for a bench model."""
+    from oracle import aasist_oracle as O
+    if model_name == "AASIST2":
+        from oracle import aasist2_oracle as O2
+        cfg = O2.CONFIGS[model_name]
+        return cfg, lambda sd, x, bank: O2.aasist2_forward(sd, cfg, x, None, None, bank)
+    cfg = O.CONFIGS[model_name]
+    return cfg, lambda sd, x, bank: O.forward(model_name, sd, cfg, x, None, bank)
 
 
 def cpu_oracle_throughput(model_name: str, n_utt: int, repeats: int, warmup: int = 1):
@@ -97,13 +109,13 @@ def cpu_oracle_throughput(model_name: str, n_utt: int, repeats: int, warmup: int
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
     sd = torch.load(aasist_b200.weights_path(model_name), map_location="cpu")
-    cfg = O.CONFIGS[model_name]
+    cfg, fwd = _oracle_forward(model_name)
     x = O.white_noise(n_utt, L_SAMPLES, 1234)
     bank = O.sinc_filterbank(cfg["filts"][0], cfg["first_conv"])
     times = []
     for i in range(warmup + repeats):
         t0 = time.perf_counter()
-        O.forward(model_name, sd, cfg, x, None, bank)
+        fwd(sd, x, bank)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
@@ -469,7 +481,7 @@ def run_native(args):
         "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32" if precision == "fp32" else f"{precision}(split)+f32acc",
         "data": "synthetic",
-        "config": {"workload": f"{name} (config/{name}.conf, shipped {name}.pth) eval scoring forward, "
+        "config": {"workload": f"{name} (config/{name}.conf, {aasist_b200.WEIGHTS[name]}) eval scoring forward, "
                                f"batch {B} per GPU, L={L_SAMPLES}",
                    "model_name": name, "batch_per_gpu": B, "global_batch": B * world, "samples": L_SAMPLES,
                    "precision": precision,
@@ -481,7 +493,7 @@ def run_native(args):
         "kernels": [{"kernel": r["kernel"], "launches": r["launches"], "ms_per_step": r["ms"] / n_prof,
                      "share": r["ms"] / total_kernel_ms} for r in prof],
         "kernels_note": f"per-launch CUDA events from a separate untimed pass of {n_prof} steps",
-        "algorithmic_tflops": value * (FLOPS_PER_UTT[name] if L_SAMPLES == 64600 else
+        "algorithmic_tflops": value * (FLOPS_PER_UTT[name] if L_SAMPLES == 64600 and name in FLOPS_PER_UTT else
                                        2.0 * sum(workmodel.stage_macs(name, L_SAMPLES).values())) / 1e12,
         "lib_sha16": _lib_sha16(),
     }
