@@ -17,8 +17,8 @@ AASIST-L.conf: the shipped checkpoints) gets the (2,3) ``Residual_block`` encode
 
 Input range (precision ``"f16x3"``): waveforms are expected in [-1, 1] like the reference's
 ``soundfile`` floats; fp16 operand pairs saturate at +-65504, so an un-normalised (e.g. int16-scale)
-waveform must be scaled first or scored with ``precision="fp32"``.  Utterances longer than ~25 s
-(> ~150 temporal nodes) exceed the graph kernel's shared memory and raise.
+waveform must be scaled first or scored with ``precision="fp32"``.  Utterances longer than ~18 s
+(> 132 temporal nodes, ~291 000 samples) exceed the graph kernel's shared memory and raise.
 """
 from __future__ import annotations
 
