@@ -51,6 +51,7 @@ struct Block0Params {
   const float* b2;         // [32] conv2 bias + downsample bias
   int B, W, J, Wo, Jn, n_jt, n_slots;
   long long* stats;        // optional: per-CTA MMA-warp wait cycles [total, a1full, d1empty, vfull, tempty, dsfull]
+  int collector;           // A-operand collector reuse between the two a_hi products (tc.cuh collector_mask)
 };
 
 __device__ __forceinline__ uint64_t b0_desc_noswz(uint32_t smem_addr, uint32_t sbo = 256) {   // LBO 128 B
@@ -176,6 +177,7 @@ block0_tc_kernel(const Block0Params p) {
     int g2 = 0, nds = 0;                   // conv2 steps issued (step g starts an output row in slot g & 1)
     long long w_a1 = 0, w_d1 = 0, w_vf = 0, w_te = 0, w_ds = 0;
     const long long t_begin = AASIST_CLOCK();
+    const bool coll = p.collector != 0;
 
     auto issue_conv1_row = [&]() {         // one v row: all three pool phases in three N=96 MMAs
       const int ka = n1 % kB0NA1, kd = n1 % kB0ND1;
@@ -187,9 +189,15 @@ block0_tc_kernel(const Block0Params p) {
         const uint64_t a_hi = b0_desc_noswz(a_tile, 512), a_lo = b0_desc_noswz(a_tile + 256, 512);   // K slices 0, 1
         const uint32_t d = tmem_base + (uint32_t)(D1_COL0 + 96 * kd);
         constexpr uint32_t ID96 = umma_idesc_f16(128, 96);
-        umma_f16(d, a_hi, b0_desc_noswz(b1_addr), ID96, 0);                 // z_hi * w_hi + bias_hi
-        umma_f16(d, a_lo, b0_desc_noswz(b1_addr + 3 * 1024), ID96, 1);      // z_lo * w_hi
-        umma_f16(d, a_hi, b0_desc_noswz(b1_addr + 6 * 1024), ID96, 1);      // z_hi * w_lo + bias_lo
+        if (coll) {
+          umma_f16_keep(d, a_hi, b0_desc_noswz(b1_addr), ID96, 0);            // z_hi * w_hi + bias_hi
+          umma_f16_reuse(d, a_hi, b0_desc_noswz(b1_addr + 6 * 1024), ID96, 1); // z_hi * w_lo + bias_lo (A from the collector)
+          umma_f16(d, a_lo, b0_desc_noswz(b1_addr + 3 * 1024), ID96, 1);      // z_lo * w_hi
+        } else {
+          umma_f16(d, a_hi, b0_desc_noswz(b1_addr), ID96, 0);
+          umma_f16(d, a_lo, b0_desc_noswz(b1_addr + 3 * 1024), ID96, 1);
+          umma_f16(d, a_hi, b0_desc_noswz(b1_addr + 6 * 1024), ID96, 1);
+        }
         umma_commit(&a1empty[ka]);
         umma_commit(&d1full[kd]);
       }
@@ -205,9 +213,15 @@ block0_tc_kernel(const Block0Params p) {
       const uint64_t w_hi = umma_desc_sw128(w_row), w_lo = umma_desc_sw128(w_row + 64);
 #pragma unroll
       for (int kc = 0; kc < 2; ++kc) {
-        umma_f16(d_tmem, a_hi + 2 * kc, w_hi + 2 * kc, idesc, 1);
-        umma_f16(d_tmem, a_lo + 2 * kc, w_hi + 2 * kc, idesc, 1);
-        umma_f16(d_tmem, a_hi + 2 * kc, w_lo + 2 * kc, idesc, 1);
+        if (coll) {
+          umma_f16_keep(d_tmem, a_hi + 2 * kc, w_hi + 2 * kc, idesc, 1);
+          umma_f16_reuse(d_tmem, a_hi + 2 * kc, w_lo + 2 * kc, idesc, 1);  // same A: taken from the collector
+          umma_f16(d_tmem, a_lo + 2 * kc, w_hi + 2 * kc, idesc, 1);
+        } else {
+          umma_f16(d_tmem, a_hi + 2 * kc, w_hi + 2 * kc, idesc, 1);
+          umma_f16(d_tmem, a_lo + 2 * kc, w_hi + 2 * kc, idesc, 1);
+          umma_f16(d_tmem, a_hi + 2 * kc, w_lo + 2 * kc, idesc, 1);
+        }
       }
     };
     auto issue_group = [&](uint32_t a_slot, uint32_t wb, int phi) {
@@ -250,8 +264,13 @@ block0_tc_kernel(const Block0Params p) {
           {
             const uint64_t a = b0_desc_noswz(ds_base + (uint32_t)(kq * kB0DsBytes));
             const uint32_t off = (g & 1) ? 0u : 1024u;
-            umma_f16(tmem_base, a, b0_desc_noswz(bds_addr + off), umma_idesc_f16(128, 192), 1);          // z_hi*w_hi + z_lo*w_hi
-            umma_f16(tmem_base, a, b0_desc_noswz(bds_addr + 7 * 1024 + off), umma_idesc_f16(128, 192), 1);   // z_hi*w_lo
+            if (coll) {
+              umma_f16_keep(tmem_base, a, b0_desc_noswz(bds_addr + off), umma_idesc_f16(128, 192), 1);      // z_hi*w_hi + z_lo*w_hi
+              umma_f16_reuse(tmem_base, a, b0_desc_noswz(bds_addr + 7 * 1024 + off), umma_idesc_f16(128, 192), 1);   // z_hi*w_lo
+            } else {
+              umma_f16(tmem_base, a, b0_desc_noswz(bds_addr + off), umma_idesc_f16(128, 192), 1);
+              umma_f16(tmem_base, a, b0_desc_noswz(bds_addr + 7 * 1024 + off), umma_idesc_f16(128, 192), 1);
+            }
             umma_commit(&dsempty[kq]);
           }
             ++nds;
@@ -561,6 +580,7 @@ int launch_block0_tc(aasist_handle* h, int sm_count, const uint8_t* wimg, const 
   want_stats = 0;   // the instrumentation is compiled in only by tools/variant_build.sh -DAASIST_KERNEL_STATS
 #endif
   p.stats = nullptr;
+  p.collector = (collector_mask() >> 1) & 1;
   if (want_stats) {
     AASIST_CUDA(cudaMalloc(&p.stats, sizeof(long long) * 8 * grid));
     AASIST_CUDA(cudaMemset(p.stats, 0, sizeof(long long) * 8 * grid));

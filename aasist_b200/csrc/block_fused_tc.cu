@@ -49,6 +49,7 @@ struct BlockFusedParams {
   int B, W, J, Wo, Jn, n_jt, n_vslots, n_xslots, Co;
   long long* stats;        // optional: MMA-warp wait cycles per CTA [total, d1empty, xfull, vfull, tempty]
   int products;            // 3 (f16x3) or 2 (f16x2: no a_hi * w_lo weight-correction product)
+  int collector;           // A-operand collector reuse between the two a_hi products (tc.cuh collector_mask)
 };
 
 __device__ __forceinline__ float bf_ex2(float x) {
@@ -188,7 +189,7 @@ block_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const BlockFusedP
 
     // one A tile (128 rows x [hi|lo]) against `ntaps` merged column taps x both slots: N = 64 * ntaps,
     // three fp16 products, everything accumulates (the slots were zeroed when they were drained)
-    const bool three = p.products == 3;
+    const bool three = p.products == 3, coll = p.collector != 0;
     auto mma3 = [&](uint32_t d_tmem, uint32_t a_row, uint32_t w_row, int ntaps) {
       const uint32_t idesc = ntaps == 3 ? umma_idesc_f16(128, 192)
                                         : (ntaps == 2 ? umma_idesc_f16(128, 128) : umma_idesc_f16(128, 64));
@@ -196,9 +197,15 @@ block_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const BlockFusedP
       const uint64_t w_hi = umma_desc_sw128(w_row), w_lo = umma_desc_sw128(w_row + 64);
 #pragma unroll
       for (int kc = 0; kc < 2; ++kc) {
-        umma_f16(d_tmem, a_hi + 2 * kc, w_hi + 2 * kc, idesc, 1);
-        umma_f16(d_tmem, a_lo + 2 * kc, w_hi + 2 * kc, idesc, 1);
-        if (three) umma_f16(d_tmem, a_hi + 2 * kc, w_lo + 2 * kc, idesc, 1);
+        if (three && coll) {     // a_hi * w_hi and a_hi * w_lo back to back: the second takes A from the collector
+          umma_f16_keep(d_tmem, a_hi + 2 * kc, w_hi + 2 * kc, idesc, 1);
+          umma_f16_reuse(d_tmem, a_hi + 2 * kc, w_lo + 2 * kc, idesc, 1);
+          umma_f16(d_tmem, a_lo + 2 * kc, w_hi + 2 * kc, idesc, 1);
+        } else {
+          umma_f16(d_tmem, a_hi + 2 * kc, w_hi + 2 * kc, idesc, 1);
+          umma_f16(d_tmem, a_lo + 2 * kc, w_hi + 2 * kc, idesc, 1);
+          if (three) umma_f16(d_tmem, a_hi + 2 * kc, w_lo + 2 * kc, idesc, 1);
+        }
       }
     };
     // pool phase s is served by column tap dw with (s + dw - 1) == phi (mod 3), from A rows shifted by
@@ -469,6 +476,7 @@ int launch_block_fused_tc(aasist_handle* h, int sm_count, const char* name, cons
 #endif
   p.stats = nullptr;
   p.products = h->cfg.precision == AASIST_PREC_F16X2 ? 2 : 3;
+  p.collector = (collector_mask() >> 2) & 1;
   if (want_stats) {
     AASIST_CUDA(cudaMalloc(&p.stats, sizeof(long long) * 16 * grid));
     AASIST_CUDA(cudaMemset(p.stats, 0, sizeof(long long) * 16 * grid));

@@ -67,6 +67,7 @@ struct ConvTcParams {
   int wimg_bytes;
   long long* stats;        // optional: MMA-warp wait cycles per CTA [total, full(TMA), tempty(epilogue)]
   int products;            // 3 = a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (f16x3); 2 = without the weight correction (f16x2)
+  int collector;           // A-operand collector reuse between the two a_hi products (tc.cuh collector_mask)
 };
 
 struct ConvTc {            // one convolution's packed device state
@@ -322,9 +323,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
       for (int kc = 0; kc < KC; ++kc) {               // +32 B per K chunk == +2 in the descriptor
         if (kc < nkc) {
-          umma_f16(d_tmem, a_hi + 2 * kc, w_hi + 2 * kc, idesc, (kc > 0 || !fresh) ? 1u : 0u);
-          umma_f16(d_tmem, a_lo + 2 * kc, w_hi + 2 * kc, idesc, 1);
-          if (p.products == 3) umma_f16(d_tmem, a_hi + 2 * kc, w_lo + 2 * kc, idesc, 1);
+          const uint32_t acc0 = (kc > 0 || !fresh) ? 1u : 0u;
+          if (p.products == 3 && p.collector) {   // a_hi * w_hi, a_hi * w_lo back to back: A from the collector
+            umma_f16_keep(d_tmem, a_hi + 2 * kc, w_hi + 2 * kc, idesc, acc0);
+            umma_f16_reuse(d_tmem, a_hi + 2 * kc, w_lo + 2 * kc, idesc, 1);
+            umma_f16(d_tmem, a_lo + 2 * kc, w_hi + 2 * kc, idesc, 1);
+          } else {
+            umma_f16(d_tmem, a_hi + 2 * kc, w_hi + 2 * kc, idesc, acc0);
+            umma_f16(d_tmem, a_lo + 2 * kc, w_hi + 2 * kc, idesc, 1);
+            if (p.products == 3) umma_f16(d_tmem, a_hi + 2 * kc, w_lo + 2 * kc, idesc, 1);
+          }
         }
       }
     };
@@ -873,6 +881,7 @@ static int launch_conv(aasist_handle* h, const char* name, const CUtensorMap& tm
 #endif
   p.stats = nullptr;
   p.products = h->cfg.precision == AASIST_PREC_F16X2 ? 2 : 3;
+  p.collector = (collector_mask() >> (CPI == 32 ? 3 : 4)) & 1;
   if (want_stats) {
     AASIST_CUDA(cudaMalloc(&p.stats, sizeof(long long) * 4 * grid));
     AASIST_CUDA(cudaMemset(p.stats, 0, sizeof(long long) * 4 * grid));

@@ -44,6 +44,7 @@ constexpr float kFtScale = 1024.f;            // 2^10 on both operands
 struct FrontTcParams {
   const float* x;          // (B, L)
   float* out;              // (B, 23, Wp)
+  int collector;           // A-operand collector reuse between the two a_hi products
   const uint8_t* bimg;     // filter operand image: [hi|lo][kc][208 rows x 32 B], no-swizzle canonical
   int B, L, Wp, n_tiles_per_utt;
   float bn_scale, bn_shift;
@@ -185,9 +186,15 @@ sinc_frontend_tc_kernel(const FrontTcParams p) {
           const uint64_t a_lo = umma_desc_noswz(a_base + (uint32_t)((2 * kc + 1) * kFtAChunk));
           const uint64_t b_hi = umma_desc_noswz(b_base + (uint32_t)(kc * kFtBChunk));
           const uint64_t b_lo = umma_desc_noswz(b_base + (uint32_t)((kFtKC + kc) * kFtBChunk));
-          umma_f16(d, a_hi, b_hi, IDESC, kc > 0 ? 1u : 0u);
-          umma_f16(d, a_lo, b_hi, IDESC, 1);
-          umma_f16(d, a_hi, b_lo, IDESC, 1);
+          if (p.collector) {
+            umma_f16_keep(d, a_hi, b_hi, IDESC, kc > 0 ? 1u : 0u);
+            umma_f16_reuse(d, a_hi, b_lo, IDESC, 1);                    // same A: taken from the collector
+            umma_f16(d, a_lo, b_hi, IDESC, 1);
+          } else {
+            umma_f16(d, a_hi, b_hi, IDESC, kc > 0 ? 1u : 0u);
+            umma_f16(d, a_lo, b_hi, IDESC, 1);
+            umma_f16(d, a_hi, b_lo, IDESC, 1);
+          }
           umma_commit(&aempty[kc]);
         }
       }
@@ -360,6 +367,7 @@ int launch_frontend_tc(aasist_handle* h, const uint8_t* bimg, int sm_count, cons
   want_stats = 0;   // the instrumentation is compiled in only by tools/variant_build.sh -DAASIST_KERNEL_STATS
 #endif
   p.stats = nullptr;
+  p.collector = collector_mask() & 1;
   if (want_stats) {
     AASIST_CUDA(cudaMalloc(&p.stats, sizeof(long long) * 4 * grid));
     AASIST_CUDA(cudaMemset(p.stats, 0, sizeof(long long) * 4 * grid));

@@ -139,6 +139,39 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The same MMA with the A-operand collector: `_keep` (collector::a::fill) retains the A tile it fetched from shared
+// memory, `_reuse` (collector::a::lastuse) takes A from the collector instead of shared memory -- legal only directly
+// after a `_keep` MMA with the SAME A descriptor.  The split products a_hi*w_hi and a_hi*w_lo share their A operand,
+// so issuing them back to back saves one of the three 4 KB A fetches per K chunk (SASS: UTCHMMA .A_KEEP / .A_REUSE).
+#ifndef AASIST_NO_COLLECTOR
+__device__ __forceinline__ void umma_f16_keep(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_reuse(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+#else
+__device__ __forceinline__ void umma_f16_keep(uint32_t d, uint64_t a, uint64_t b, uint32_t i, uint32_t acc) {
+  umma_f16(d, a, b, i, acc);
+}
+__device__ __forceinline__ void umma_f16_reuse(uint32_t d, uint64_t a, uint64_t b, uint32_t i, uint32_t acc) {
+  umma_f16(d, a, b, i, acc);
+}
+#endif
 // arrive on an mbarrier once every MMA issued so far by this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))

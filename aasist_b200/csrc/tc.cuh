@@ -3,9 +3,24 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
+constexpr int kCollectorDefault = 0x14;   // fused 32->32 block + conv_tc with 64 input channels (measured: profiles/README.md)
+
 namespace aasist {
+// A-operand collector reuse (ptx.cuh umma_f16_keep / _reuse) per kernel family; bit 0 sinc front end, 1 block 0,
+// 2 fused 32->32 block, 3 conv_tc with 32 input channels, 4 conv_tc with 64 input channels.  The default is what
+// measured faster on B200 (profiles/README.md); AASIST_COLLECTOR=<mask> overrides it for A/B runs.
+inline int collector_mask() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("AASIST_COLLECTOR");
+    v = e ? atoi(e) : kCollectorDefault;
+  }
+  return v;
+}
 int tc_finalize(aasist_handle* h);
 void tc_destroy(aasist_handle* h);
 size_t tc_workspace_bytes(const aasist_handle* h, int B, int L);

@@ -149,8 +149,10 @@ def test_error_behaviour_matches_reference_contract():
     m(torch.zeros(1, 2315, device=g.DEV))               # shortest valid length
     with pytest.raises(RuntimeError):
         m(torch.zeros(2, 64600))                        # CPU tensor: no fallback
-    with pytest.raises(NotImplementedError):
-        m(torch.zeros(1, 64600, device=g.DEV), Freq_aug=True)
+    m.train()
+    with pytest.raises(NotImplementedError):            # eval-mode scoring only (reference main.py:354)
+        m(torch.zeros(1, 64600, device=g.DEV))
+    m.eval()
     r = g.native_model("RawGAT-ST")
     with pytest.raises(RuntimeError):                   # hard-wired to 64600 (Linear(14,12)/(23,12))
         r(torch.zeros(1, 32000, device=g.DEV))
