@@ -85,6 +85,7 @@ SIGNATURES = {
     "aasist_graph": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "aasist_launch_count": (C.c_int64, [C.c_void_p]),
+    "aasist_input_range_exceeded": (C.c_int, [C.c_void_p, C.c_int32]),
     "aasist_profile_enable": (C.c_int, [C.c_void_p, C.c_int32]),
     "aasist_profile_report": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64, C.c_int32]),
 }

@@ -317,6 +317,7 @@ static std::vector<float> pack_w33(const std::vector<float>& w, int ci, int co, 
 
 static int pack_res2_block(aasist_handle* h, const std::string& p, int index, int ci, int co, Res2BlockF32& blk) {
   const int cop = co <= 32 ? 32 : 64;
+  blk.index = index;
   blk.ci = ci;
   blk.co = co;
   blk.first = index == 0;
@@ -361,7 +362,31 @@ static int pack_res2_block(aasist_handle* h, const std::string& p, int index, in
   }
   blk.n_groups = (int)blk.groups.size();
   blk.n_levels = levels;
+  // launch plan: per dependency level, splits bucketed by the register-accumulator width of the kernel variant
+  auto nreg_of = [](int n) {
+    const int widths[] = {1, 2, 4, 6, 8, 12, 16, 32, 64};
+    for (int w : widths)
+      if (n <= w) return w;
+    return 64;
+  };
+  blk.launches.clear();
+  std::vector<int> lvl_groups;
+  for (int level = 0; level < levels; ++level) {
+    const int widths[] = {1, 2, 4, 6, 8, 12, 16, 32, 64};
+    for (int w : widths) {
+      Res2Launch L{level, w, 0, (int)lvl_groups.size(), 0, 0};
+      for (size_t g = 0; g < blk.groups.size(); ++g)
+        if (blk.groups[g].level == level && nreg_of(blk.groups[g].n) == w) {
+          lvl_groups.push_back((int)g);
+          L.n_max = std::max(L.n_max, blk.groups[g].n);
+          L.n_tot += blk.groups[g].n;
+          ++L.count;
+        }
+      if (L.count) blk.launches.push_back(L);
+    }
+  }
   int rc;
+  if ((rc = upload_i(&blk.lvl_groups_dev, lvl_groups))) return rc;
   {
     if (blk.groups_dev) cudaFree(blk.groups_dev);
     blk.groups_dev = nullptr;
@@ -387,8 +412,15 @@ static int pack_res2_block(aasist_handle* h, const std::string& p, int index, in
   if ((rc = upload(&blk.se0, P(h, p + ".se.fc.0.weight")))) return rc;
   if ((rc = upload(&blk.se2, P(h, p + ".se.fc.2.weight")))) return rc;
   if (blk.downsample) {
-    if ((rc = upload(&blk.wd, P(h, p + ".conv_downsample.weight")))) return rc;
-    if ((rc = upload(&blk.bd, P(h, p + ".conv_downsample.bias")))) return rc;
+    const auto &wd = P(h, p + ".conv_downsample.weight"), &bd = P(h, p + ".conv_downsample.bias");
+    std::vector<float> pwd((size_t)ci * 3 * cop, 0.f), pbd(cop, 0.f);
+    for (int o = 0; o < co; ++o) {
+      for (int i = 0; i < ci; ++i)
+        for (int t = 0; t < 3; ++t) pwd[((size_t)i * 3 + t) * cop + o] = wd[((size_t)o * ci + i) * 3 + t];
+      pbd[o] = bd[o];
+    }
+    if ((rc = upload(&blk.wd, pwd))) return rc;
+    if ((rc = upload(&blk.bd, pbd))) return rc;
   }
   return 0;
 }
@@ -823,7 +855,7 @@ int aasist_destroy(aasist_handle* h) {
     }
   for (int i = 0; i < 6; ++i) {
     Res2BlockF32& r = h->res2[i];
-    cudaFree(r.groups_dev); cudaFree(r.bn1); cudaFree(r.gw); cudaFree(r.gb); cudaFree(r.gw_off); cudaFree(r.bn2);
+    cudaFree(r.groups_dev); cudaFree(r.lvl_groups_dev); cudaFree(r.bn1); cudaFree(r.gw); cudaFree(r.gb); cudaFree(r.gw_off); cudaFree(r.bn2);
     cudaFree(r.wcat); cudaFree(r.bcat); cudaFree(r.se0); cudaFree(r.se2); cudaFree(r.wd); cudaFree(r.bd);
     ConvBlock33F32& b = h->blocks33[i];
     cudaFree(b.w1); cudaFree(b.b1); cudaFree(b.w2); cudaFree(b.b2); cudaFree(b.wd);
@@ -843,6 +875,7 @@ int aasist_destroy(aasist_handle* h) {
   cudaFree(h->stage_meta);
   cudaFree(h->own_ws);
   cudaFree(h->front_bimg_masked);
+  if (h->range_flag) cudaFreeHost(h->range_flag);
   delete h;
   return AASIST_OK;
 }
@@ -1387,6 +1420,13 @@ int aasist_graph(aasist_handle* h, const float* e, const float* e2, int32_t B, i
 }
 
 int64_t aasist_launch_count(const aasist_handle* h) { return h ? h->launches : 0; }
+
+int aasist_input_range_exceeded(aasist_handle* h, int32_t reset) {
+  if (!h || !h->range_flag) return 0;
+  const int v = *reinterpret_cast<volatile int*>(h->range_flag);
+  if (reset) *h->range_flag = 0;
+  return v != 0;
+}
 
 int aasist_profile_enable(aasist_handle* h, int32_t enable) {
   if (!h) return AASIST_E_INVALID;

@@ -177,7 +177,8 @@ block0_tc_kernel(const Block0Params p) {
     int g2 = 0, nds = 0;                   // conv2 steps issued (step g starts an output row in slot g & 1)
     long long w_a1 = 0, w_d1 = 0, w_vf = 0, w_te = 0, w_ds = 0;
     const long long t_begin = AASIST_CLOCK();
-    const bool coll = p.collector != 0;
+    const bool coll = (p.collector & 1) != 0;      // conv2 (32 -> 32) MMAs
+    const bool coll1 = (p.collector & 2) != 0;     // conv1 / downsample MMAs (K = 16 im2col tiles)
 
     auto issue_conv1_row = [&]() {         // one v row: all three pool phases in three N=96 MMAs
       const int ka = n1 % kB0NA1, kd = n1 % kB0ND1;
@@ -189,7 +190,7 @@ block0_tc_kernel(const Block0Params p) {
         const uint64_t a_hi = b0_desc_noswz(a_tile, 512), a_lo = b0_desc_noswz(a_tile + 256, 512);   // K slices 0, 1
         const uint32_t d = tmem_base + (uint32_t)(D1_COL0 + 96 * kd);
         constexpr uint32_t ID96 = umma_idesc_f16(128, 96);
-        if (coll) {
+        if (coll1) {
           umma_f16_keep(d, a_hi, b0_desc_noswz(b1_addr), ID96, 0);            // z_hi * w_hi + bias_hi
           umma_f16_reuse(d, a_hi, b0_desc_noswz(b1_addr + 6 * 1024), ID96, 1); // z_hi * w_lo + bias_lo (A from the collector)
           umma_f16(d, a_lo, b0_desc_noswz(b1_addr + 3 * 1024), ID96, 1);      // z_lo * w_hi
@@ -264,7 +265,7 @@ block0_tc_kernel(const Block0Params p) {
           {
             const uint64_t a = b0_desc_noswz(ds_base + (uint32_t)(kq * kB0DsBytes));
             const uint32_t off = (g & 1) ? 0u : 1024u;
-            if (coll) {
+            if (coll1) {
               umma_f16_keep(tmem_base, a, b0_desc_noswz(bds_addr + off), umma_idesc_f16(128, 192), 1);      // z_hi*w_hi + z_lo*w_hi
               umma_f16_reuse(tmem_base, a, b0_desc_noswz(bds_addr + 7 * 1024 + off), umma_idesc_f16(128, 192), 1);   // z_hi*w_lo
             } else {
@@ -580,7 +581,7 @@ int launch_block0_tc(aasist_handle* h, int sm_count, const uint8_t* wimg, const 
   want_stats = 0;   // the instrumentation is compiled in only by tools/variant_build.sh -DAASIST_KERNEL_STATS
 #endif
   p.stats = nullptr;
-  p.collector = (collector_mask() >> 1) & 1;
+  p.collector = ((collector_mask() >> 1) & 1) | (((collector_mask() >> 5) & 1) << 1);
   if (want_stats) {
     AASIST_CUDA(cudaMalloc(&p.stats, sizeof(long long) * 8 * grid));
     AASIST_CUDA(cudaMemset(p.stats, 0, sizeof(long long) * 8 * grid));

@@ -49,11 +49,18 @@ struct Res2Group {
   int level;        // 0 = reads only the block input; l > 0 = also adds the raw output of the previous split
   int feeds_next;   // its raw conv output is the next split's addend (keep it in the `raw` scratch)
 };
+struct Res2Launch {   // one split-conv launch: the splits of one dependency level that share an accumulator width
+  int level, nreg, n_max, first, count;     // lvl_groups[first .. first+count)
+  int n_tot;                                // channels of all its splits (shared-memory tile rows)
+};
 struct Res2BlockF32 {
+  int index = 0;           // encoder block number (kernel names in the per-launch profile)
   int ci = 0, co = 0;
   bool first = false, downsample = false;
   int n_groups = 0, n_levels = 0;
   std::vector<Res2Group> groups;     // host copy
+  std::vector<Res2Launch> launches;  // in dependency order
+  int* lvl_groups_dev = nullptr;     // split indices, launch by launch
   Res2Group* groups_dev = nullptr;
   float* bn1 = nullptr;    // [2][ci]  scale, shift of bn1 (LIVE in this block, AASIST.py:611-613); null when first
   float* gw = nullptr;     // split convs, concatenated: group g at gw_off[g]: [n][n][3][3] (out,in,kh,kw)
@@ -65,8 +72,8 @@ struct Res2BlockF32 {
   float* se0 = nullptr;    // se.fc.0.weight (co/16, co)
   float* se2 = nullptr;    // se.fc.2.weight (co, co/16)
   int se_hidden = 0;
-  float* wd = nullptr;     // conv_downsample [co][ci][3] or null
-  float* bd = nullptr;     // [co]
+  float* wd = nullptr;     // conv_downsample [ci][3][cop] or null
+  float* bd = nullptr;     // [cop]
 };
 
 // the fork's 3x3 Residual_block (models/AASIST.py:672-725), fp32 CUDA-core path
@@ -207,6 +214,8 @@ struct aasist_handle {
   cudaEvent_t copy_done[2] = {nullptr, nullptr}, start_ev = nullptr;
   // scratch owned by the handle (aasist_forward_ex with workspace == NULL, forward_host, scoring stream)
   void* own_ws = nullptr; size_t own_ws_bytes = 0;
+  // input-range guard of the f16x3 front end: pinned, device-mapped flag (aasist_input_range_exceeded)
+  int* range_flag = nullptr;
   // Freq_aug: masked copy of the tensor-core filter operand (frontend_tc.cu)
   uint8_t* front_bimg_masked = nullptr;
   // scoring stream (aasist_score_begin / submit / finish)

@@ -45,6 +45,7 @@ struct FrontTcParams {
   const float* x;          // (B, L)
   float* out;              // (B, 23, Wp)
   int collector;           // A-operand collector reuse between the two a_hi products
+  int* range_flag;         // host-mapped: set to 1 when a sample leaves the fp16 operand range (|x| * 2^10 > 65504)
   const uint8_t* bimg;     // filter operand image: [hi|lo][kc][208 rows x 32 B], no-swizzle canonical
   int B, L, Wp, n_tiles_per_utt;
   float bn_scale, bn_shift;
@@ -247,6 +248,9 @@ sinc_frontend_tc_kernel(const FrontTcParams p) {
         const int i = ptid + 32 * kFtProdWarps * q;
         if (i < kFtSeg + 1) {
           const float vc = fminf(fmaxf(pre[q] * kFtScale, -65504.f), 65504.f);
+          // un-normalised input (e.g. int16-scale samples): the operand saturates and the logits are wrong without
+          // any error -- raise the host-visible flag (a store over PCIe on this rare path only)
+          if (fabsf(pre[q]) * kFtScale > 65504.f) *reinterpret_cast<volatile int*>(p.range_flag) = 1;
           const __half h = __float2half_rn(vc);
           const __half l = __float2half_rn(vc - __half2float(h));
           xh0[i] = h;
@@ -368,6 +372,11 @@ int launch_frontend_tc(aasist_handle* h, const uint8_t* bimg, int sm_count, cons
 #endif
   p.stats = nullptr;
   p.collector = collector_mask() & 1;
+  if (!h->range_flag) {
+    AASIST_CUDA(cudaHostAlloc(&h->range_flag, sizeof(int), cudaHostAllocMapped));
+    *h->range_flag = 0;
+  }
+  p.range_flag = h->range_flag;
   if (want_stats) {
     AASIST_CUDA(cudaMalloc(&p.stats, sizeof(long long) * 4 * grid));
     AASIST_CUDA(cudaMemset(p.stats, 0, sizeof(long long) * 4 * grid));

@@ -334,6 +334,20 @@ class _NativeModel(nn.Module):
         _lib.check(lib.aasist_topk_layout(self._handle, length, C.byref(n), nk))
         return [(nk[2 * i], nk[2 * i + 1]) for i in range(n.value)]
 
+    def check_input_range(self) -> bool:
+        """True (and a RuntimeWarning) when a forward that has completed since the last check saw samples outside
+        the f16x3 operand range (|x| > 63.96: an un-normalised waveform).  Called after every synchronising entry
+        point and, for the asynchronous ``forward``, at the start of the next call."""
+        if self._handle is None or self.precision == "fp32":
+            return False
+        if _lib.load().aasist_input_range_exceeded(self._handle, 1):
+            import warnings
+            warnings.warn("aasist_b200: input samples exceed the fp16 operand range of precision "
+                          f"'{self.precision}' (|x| > 63.96); the logits of that batch are wrong. Normalise the "
+                          "waveform to [-1, 1] or use precision='fp32'.", RuntimeWarning, stacklevel=3)
+            return True
+        return False
+
     def _forward_native(self, x: Tensor, freq_mask: Optional[Tuple[int, int]] = None,
                         speaker_embedding: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
         if x.dim() == 3 and x.size(1) == 1:                  # AASIST.py:816-817 accepts (B,1,L)
@@ -352,6 +366,7 @@ class _NativeModel(nn.Module):
         if p0.device != dev:
             raise RuntimeError(f"model parameters are on {p0.device}, input on {dev}")
         self._ensure_handle(dev)
+        self.check_input_range()                  # of the forwards that have completed so far
         x = x.detach().to(torch.float32).contiguous()
         B, L = x.shape
         opts = None
@@ -401,6 +416,7 @@ class _NativeModel(nn.Module):
             stream = torch.cuda.current_stream(dev).cuda_stream
             _lib.check(lib.aasist_forward_host(self._handle, x_host.data_ptr(), B, L,
                                                last_hidden.data_ptr(), output.data_ptr(), stream))
+        self.check_input_range()
         return last_hidden, output
 
     # -- input staging (reference data_utils.py:45-52 `pad`, applied per utterance at :208) -----------
@@ -518,6 +534,7 @@ class _NativeModel(nn.Module):
             got = _lib.check(lib.aasist_score_finish(self._handle, out.data_ptr(),
                                                      hid.data_ptr() if hid is not None else None, None))
         assert got == n, (got, n)
+        self.check_input_range()
         self.__dict__["_score_keep"], self.__dict__["_score_n"] = [], 0
         return (hid, out) if want_hidden else out
 

@@ -48,6 +48,10 @@ def stage_macs(name: str, length: int = 64600):
 def kernel_flops(name: str, kernel: str, batch: int, length: int = 64600) -> float:
     """Algorithmic FLOPs per forward of all launches reported under `kernel`."""
     m = stage_macs(name, length)
+    if kernel.startswith("enc") and ".res2_" in kernel:     # Res2Net: "enc{i}.res2_split_convs_f32" / "...conv_cat..."
+        blk = kernel.split(".")[0]
+        macs = m[f"{blk}.splits"] if "split" in kernel else m[f"{blk}.conv_cat"] + m[f"{blk}.ds"]
+        return 2.0 * macs * batch
     if kernel.startswith("enc") and "." in kernel:          # "enc{i}.conv1[_tc]" / "enc{i}.conv2[_tc]"
         blk, conv = kernel.split(".")[0], kernel.split(".")[1]
         if conv.startswith("fused"):   # whole block in one kernel

@@ -244,6 +244,13 @@ int aasist_graph(aasist_handle* h, const float* e, const float* e2, int32_t B, i
                  float* last_hidden, float* logits, int32_t* topk_idx, float* pool_scores,
                  void* stream);
 
+/* Input-range guard of the tensor-core path.  The f16x3 front end holds a sample as an fp16 pair of x * 2^10, which
+ * saturates for |x| > 63.96: waveforms are expected in [-1, 1] (what soundfile returns), and an un-normalised one
+ * (e.g. int16-scale samples) would give wrong logits silently, where the reference's fp32 forward would not.  The
+ * kernel raises a host-visible flag when a sample saturates; this returns 1 if that happened in any forward that has
+ * COMPLETED since the last reset (call it after synchronising the stream), else 0.  fp32 handles always return 0. */
+int aasist_input_range_exceeded(aasist_handle* h, int32_t reset);
+
 /* Number of kernels this library has launched through the handle so far. */
 int64_t aasist_launch_count(const aasist_handle* h);
 

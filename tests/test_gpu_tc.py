@@ -219,3 +219,24 @@ def test_f16x2_reduced_product_mode_error_is_measured(name):
     assert all(np.isfinite(v["logit_err"]) for v in report.values())
     if name == "AASIST":
         assert worst <= 3e-3, report             # same order as single-pass TF32, 20-60x the f16x3 error
+
+
+def test_tc_input_range_guard_warns_on_unnormalised_waveforms():
+    """int16-scale samples saturate the fp16 operand pairs of the f16x3 front end; the kernel raises a
+    host-visible flag and the shim turns it into a RuntimeWarning (the fp32 path has no such limit)."""
+    import warnings
+    g = _g()
+    m = g.native_model("AASIST-L", "f16x3")
+    x = O.speech_like(2, 64600, 5)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        m.score_host(x)                                    # normal input: no warning
+    with pytest.warns(RuntimeWarning, match="exceed the fp16 operand range"):
+        m.score_host(x * 32768.0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        m.score_host(x)                                    # the flag was reset
+    m32 = g.native_model("AASIST-L", "fp32")
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        m32.score_host(x * 32768.0)
