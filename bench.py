@@ -299,11 +299,13 @@ def golden_parity(model, name: str, dev):
 
 
 def _lib_sha16() -> str:
-    import hashlib
-    from aasist_b200 import _lib
+    """Identity of the build the numbers come from: the digest of the CUDA sources + compiler flags that
+    aasist_b200/build.py stamps the library with (a hash of the binary would change with the checkout path that
+    -lineinfo embeds).  profiles/ncu_traffic.json carries the same digest."""
     try:
-        return hashlib.sha256(open(_lib.LIB_PATH, "rb").read()).hexdigest()[:16]
-    except OSError:
+        from aasist_b200 import build as _build
+        return _build._digest()[:16]
+    except Exception:
         return ""
 
 
@@ -455,11 +457,11 @@ def run_native(args):
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
             per_utt = tr.get("bytes_per_utterance", {}).get(name, {})
-            if tr.get("lib_sha16") == _lib_sha16() and top["kernel"] in per_utt:
+            if tr.get("source_digest16") == _lib_sha16() and top["kernel"] in per_utt:
                 traffic = int(per_utt[top["kernel"]] * (B / n_launch))
                 traffic_src = tr.get("source")
             elif top["kernel"] in per_utt:
-                traffic_src = "stale: profiles/ncu_traffic.json was captured on another build (%s)" % tr.get("lib_sha16")
+                traffic_src = "stale: profiles/ncu_traffic.json was captured on another build (%s)" % tr.get("source_digest16")
         except Exception:
             pass
         # tensor-pipe products per reference MAC: 3 everywhere in f16x3; f16x2 keeps 3 in the sinc stage and block 0
@@ -495,7 +497,7 @@ def run_native(args):
         "kernels_note": f"per-launch CUDA events from a separate untimed pass of {n_prof} steps",
         "algorithmic_tflops": value * (FLOPS_PER_UTT[name] if L_SAMPLES == 64600 and name in FLOPS_PER_UTT else
                                        2.0 * sum(workmodel.stage_macs(name, L_SAMPLES).values())) / 1e12,
-        "lib_sha16": _lib_sha16(),
+        "source_digest16": _lib_sha16(),
     }
     if precision != aasist_b200.model.DEFAULT_PRECISION and name in ("AASIST", "AASIST-L"):
         line["parity_vs_reference_goldens"] = golden_parity(model, name, dev)

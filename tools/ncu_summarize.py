@@ -49,16 +49,17 @@ if "--traffic-json" in sys.argv:
     a = sys.argv
     dst, model, batch = a[a.index("--traffic-json") + 1], a[a.index("--model") + 1], int(a[a.index("--batch") + 1])
     names = a[a.index("--names") + 1].split(",")
-    lib = a[a.index("--lib") + 1] if "--lib" in a else "aasist_b200/csrc/libaasist_b200.so"
     assert len(names) == len(out), (len(names), len(out))
     try:
         tr = json.load(open(dst))
     except Exception:
         tr = {}
-    sha = hashlib.sha256(open(lib, "rb").read()).hexdigest()[:16]
-    if tr.get("lib_sha16") != sha:
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from aasist_b200 import build as _build
+    sha = _build._digest()[:16]                  # sources + flags of the build the capture was taken on
+    if tr.get("source_digest16") != sha:
         tr = {"bytes_per_utterance": {}}
-    tr["lib_sha16"] = sha
+    tr["source_digest16"] = sha
     tr["source"] = f"ncu --set full, one {batch}-utterance launch per kernel ({os.path.basename(path)}); bytes = dram__bytes_read.sum + dram__bytes_write.sum"
     tr["bytes_per_utterance"][model] = {n: int((d["dram_rd"] + d["dram_wr"]) / batch) for n, d in zip(names, out)}
     tr["bytes_per_utterance"][model]["_total"] = int(sum(d["dram_rd"] + d["dram_wr"] for d in out) / batch)
