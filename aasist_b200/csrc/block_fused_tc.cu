@@ -189,8 +189,9 @@ block_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const BlockFusedP
 
     // one A tile (128 rows x [hi|lo]) against `ntaps` merged column taps x both slots: N = 64 * ntaps,
     // three fp16 products, everything accumulates (the slots were zeroed when they were drained)
-    const bool three = p.products == 3, coll = p.collector != 0;
-    auto mma3 = [&](uint32_t d_tmem, uint32_t a_row, uint32_t w_row, int ntaps) {
+    const bool three = p.products == 3;
+    const bool coll1 = (p.collector & 1) != 0, coll2 = (p.collector & 2) != 0;   // conv1 (TMA x tiles) / conv2 (v tiles)
+    auto mma3 = [&](uint32_t d_tmem, uint32_t a_row, uint32_t w_row, int ntaps, bool coll) {
       const uint32_t idesc = ntaps == 3 ? umma_idesc_f16(128, 192)
                                         : (ntaps == 2 ? umma_idesc_f16(128, 128) : umma_idesc_f16(128, 64));
       const uint64_t a_hi = umma_desc_sw128(a_row), a_lo = umma_desc_sw128(a_row + 64);
@@ -210,15 +211,15 @@ block_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const BlockFusedP
     };
     // pool phase s is served by column tap dw with (s + dw - 1) == phi (mod 3), from A rows shifted by
     // floor((s + dw - 1) / 3); taps are stored dw = 2,1,0 (8 KB each: both slots), D columns s*64
-    auto issue_group = [&](uint32_t a_slot, uint32_t wb, int phi, uint32_t d0) {
+    auto issue_group = [&](uint32_t a_slot, uint32_t wb, int phi, uint32_t d0, bool coll) {
       if (phi == 1) {
-        mma3(d0, a_slot + 128, wb, 3);
+        mma3(d0, a_slot + 128, wb, 3, coll);
       } else if (phi == 0) {
-        mma3(d0, a_slot + 128, wb + 8192, 2);
-        mma3(d0 + 128, a_slot + 256, wb, 1);
+        mma3(d0, a_slot + 128, wb + 8192, 2, coll);
+        mma3(d0 + 128, a_slot + 256, wb, 1, coll);
       } else {
-        mma3(d0 + 64, a_slot + 128, wb, 2);
-        mma3(d0, a_slot, wb + 16384, 1);
+        mma3(d0 + 64, a_slot + 128, wb, 2, coll);
+        mma3(d0, a_slot, wb + 16384, 1, coll);
       }
     };
     auto d1_claim = [&](int n) {           // v row n is about to receive its first MMA: its slot must be drained
@@ -234,7 +235,7 @@ block_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const BlockFusedP
         AASIST_TIMED_WAIT(&xfull[xslot], xphase, w_x);
         tc_fence_after_sync();
         {
-          issue_group(x_base + (uint32_t)xslot * kBfSlab, wb, phi, tmem_base + (uint32_t)D1_COL0);
+          issue_group(x_base + (uint32_t)xslot * kBfSlab, wb, phi, tmem_base + (uint32_t)D1_COL0, coll1);
           umma_commit(&xempty[xslot]);
         }
         if (++xslot == p.n_xslots) { xslot = 0; xphase ^= 1; }
@@ -254,7 +255,7 @@ block_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const BlockFusedP
         AASIST_TIMED_WAIT(&vfull[vslot], vphase, w_v);
         tc_fence_after_sync();
         {
-          issue_group(v_base + (uint32_t)vslot * kBfSlab, wb, phi, tmem_base);
+          issue_group(v_base + (uint32_t)vslot * kBfSlab, wb, phi, tmem_base, coll2);
           umma_commit(&vempty[vslot]);
         }
         if (++vslot == p.n_vslots) { vslot = 0; vphase ^= 1; }
@@ -476,7 +477,7 @@ int launch_block_fused_tc(aasist_handle* h, int sm_count, const char* name, cons
 #endif
   p.stats = nullptr;
   p.products = h->cfg.precision == AASIST_PREC_F16X2 ? 2 : 3;
-  p.collector = (collector_mask() >> 2) & 1;
+  p.collector = ((collector_mask() >> 2) & 1) | (((collector_mask() >> 6) & 1) << 1);
   if (want_stats) {
     AASIST_CUDA(cudaMalloc(&p.stats, sizeof(long long) * 16 * grid));
     AASIST_CUDA(cudaMemset(p.stats, 0, sizeof(long long) * 16 * grid));

@@ -7,12 +7,12 @@
 
 #include "common.cuh"
 
-constexpr int kCollectorDefault = 0x14;   // fused 32->32 block + conv_tc with 64 input channels (measured: profiles/README.md)
+constexpr int kCollectorDefault = 0x54;   // fused 32->32 block + conv_tc with 64 input channels (measured: profiles/README.md)
 
 namespace aasist {
 // A-operand collector reuse (ptx.cuh umma_f16_keep / _reuse) per kernel family; bit 0 sinc front end, 1 block 0
-// (conv2 MMAs; bit 5: its conv1 / downsample MMAs), 2 fused 32->32 block, 3 conv_tc with 32 input channels,
-// 4 conv_tc with 64 input channels.  The default is what
+// (conv2 MMAs; bit 5: its conv1 / downsample MMAs), 2 fused 32->32 block conv1 (bit 6: its conv2), 3 conv_tc with
+// 32 input channels, 4 conv_tc with 64 input channels.  The default is what
 // measured faster on B200 (profiles/README.md); AASIST_COLLECTOR=<mask> overrides it for A/B runs.
 inline int collector_mask() {
   static int v = -1;
