@@ -9,12 +9,17 @@
 // 3jj .. 3jj+4 of both input rows, K = 32 = [up_hi(5) dn_hi(5) 1 0(5) | up_lo(5) dn_lo(5) 0(6)], and the B
 // operands place each phase's taps on the columns it reads (N = 3 x 32): three N=96 MMAs per v row --
 // hi*w_hi (+ bias_hi on the constant-1 column), lo*w_hi, hi*w_lo (+ bias_lo) -- instead of six N=32 ones.
-// Its accumulator D1 (128 x 96, TMEM) is turned into conv2's A operand by 8 "transformer" warps:
-// tcgen05.ld -> +bias -> SELU -> zero outside [0,W) -> fp16 hi/lo -> 128B-swizzled rows of the same
-// shared-memory ring the TMA would fill for the later blocks.  conv2 then runs exactly like
-// conv_tc_kernel (strip-mined, two passes per input row, phase-split pooling), and conv_downsample
-// (1 -> 32 channels, 3 taps) is six more K=16 MMAs per output row on a second im2col tile.
-// Work item: (utterance, strip of 126 pooled columns): conv2 needs v rows j0-1 .. j0+126 = one M=128 tile.
+// Its accumulator D1 (128 x 96, TMEM) is turned into conv2's A operand by 8 "transformer" warps, and that
+// operand NEVER LEAVES TENSOR MEMORY: tcgen05.ld -> SELU -> zero outside [0,W) -> fp16 hi/lo -> tcgen05.st back
+// into the same columns (an fp32 accumulator and its fp16 pair are the same 4 bytes), and conv2 issues
+// tcgen05.mma with the A operand in TMEM (lane = tile row, 8 columns per K=16 slice).  The two taps that read
+// the neighbouring tile row (phase 2 one row up, phase 0 one row down) get their own lane-shifted copies
+// (warp shuffles + a 2 KB exchange buffer for the four quadrant boundaries).  conv2's MMAs therefore fetch only
+// their weights from shared memory: no v tiles are written to or read from it (they were 170 KB of the 330 KB
+// of shared-memory traffic per row-tile that bounded this kernel).  Otherwise conv2 runs like conv_tc_kernel
+// (strip-mined, two output rows in flight, phase-split pooling), and conv_downsample (1 -> 32 channels,
+// 3 taps) is two more K=16 MMAs per output row on a second im2col tile.
+// Work item: (utterance, strip of 126 pooled columns): tile row m = pooled column j0-1+m, rows 1..126 are stored.
 //
 // warps: 0 idle | 1 MMA issuer + TMEM owner | 2-9 epilogue | 10-17 transformers | 18-19 im2col producers
 #include <stdio.h>
@@ -29,11 +34,12 @@ namespace aasist {
 using namespace ptx;
 
 constexpr int kB0Strip = 126;               // valid pooled columns per strip
-constexpr int kB0Slab = 17 * 1024;          // one v tile (136 rows x 128 B, SWIZZLE_128B)
 constexpr int kB0A1Stride = 16 * 512;       // conv1 im2col tile of one v row: 128 rows x 64 B (K = 32), no-swizzle
                                             // canonical: 8-row groups of 512 B = 4 K-groups x (8 rows x 16 B)
 constexpr int kB0DsBytes = 16 * 256;        // downsample im2col tile: 128 rows x 32 B
-constexpr int kB0NA1 = 3, kB0ND1 = 3, kB0NDS = 3;   // rings of v rows (im2col tiles, D1 accumulators), downsample tiles
+constexpr int kB0NA1 = 3, kB0ND1 = 2, kB0NDS = 3;   // rings of v rows (im2col tiles, D1 / A-operand slots in TMEM), downsample tiles
+constexpr int kB0VCols = 160;               // TMEM columns of one v row: D1 = A(phase 0,1,2) in place [0,96), A(phase 2, row-1) [96,128), A(phase 0, row+1) [128,160)
+constexpr int kB0XchWords = 2 * 2 * 4 * 2 * 16;   // boundary exchange [parity][half][quadrant][kind][16 words]
 constexpr int kB0Threads = 640;
 constexpr int kB0ZW = 400;                  // z columns kept per row: 3*j0-4 .. 3*j0+395 (392 used)
 constexpr int kB0W2Bytes = 6 * 32 * 128;    // conv2 weight image (6 taps x [32 rows x 128 B])
@@ -49,8 +55,8 @@ struct Block0Params {
   const uint8_t* wimg;     // kB0ImgBytes
   const float* b1;         // [32] conv1 bias (bn2 folded)
   const float* b2;         // [32] conv2 bias + downsample bias
-  int B, W, J, Wo, Jn, n_jt, n_slots;
-  long long* stats;        // optional: per-CTA MMA-warp wait cycles [total, a1full, d1empty, vfull, tempty, dsfull]
+  int B, W, J, Wo, Jn, n_jt;
+  long long* stats;        // optional: per-CTA MMA-warp wait cycles [total, a1full, -, afull, tempty, dsfull]
   int collector;           // A-operand collector reuse between the two a_hi products (tc.cuh collector_mask)
 };
 
@@ -66,23 +72,12 @@ __device__ __forceinline__ float b0_ex2(float x) {
 // SELU of v given y = v * log2(e) (conv1's weights and bias are pre-scaled by log2(e) on the host, and the
 // bias rides in the MMA as a constant-1 im2col column): one MUFU.EX2 and five FMA-pipe instructions
 __device__ __forceinline__ float b0_selu_scaled(float y) {
+#ifdef B0_EXP_XF_LIGHT
+  return y;                                  // timing experiment only (tools/variant_build.sh)
+#endif
   const float e = b0_ex2(y);
   const float n = fminf(fmaf(e, kSeluScale * kSeluAlpha, -(kSeluScale * kSeluAlpha)), 0.f);
   return fmaf(fmaxf(y, 0.f), kSeluScale * 0.6931471805599453f, n);
-}
-template <bool LOWER_BOUNDED>
-__device__ __forceinline__ void b0_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  a = fminf(a, 65504.f);
-  b = fminf(b, 65504.f);
-  if (!LOWER_BOUNDED) {
-    a = fmaxf(a, -65504.f);
-    b = fmaxf(b, -65504.f);
-  }
-  const __half2 h = __floats2half2_rn(a, b);
-  const float2 f = __half22float2(h);
-  const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 __global__ void __launch_bounds__(kB0Threads, 1)
@@ -90,20 +85,18 @@ block0_tc_kernel(const Block0Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* s_w = smem;                                         // weight images
-  uint8_t* s_ring = smem + kB0SmemImgBytes;                    // v tiles
-  uint8_t* s_a1 = s_ring + (size_t)p.n_slots * kB0Slab;        // conv1 im2col ring
+  uint8_t* s_a1 = smem + kB0SmemImgBytes;                      // conv1 im2col ring
   uint8_t* s_ds = s_a1 + kB0NA1 * kB0A1Stride;                 // downsample im2col ring
   uint32_t* s_z = reinterpret_cast<uint32_t*>(s_ds + kB0NDS * kB0DsBytes);   // [3][kB0ZW] rolling rows of z as (hi,lo) fp16 words
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_z + 3 * kB0ZW);
-  uint64_t* full = bars;                   // [8]  v tile written (8 transformer warps)
-  uint64_t* empty = bars + 8;              // [8]  v tile consumed (tcgen05.commit)
+  uint32_t* s_xch = s_z + 3 * kB0ZW;       // transformer boundary rows (kB0XchWords)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_xch + kB0XchWords);
+  uint64_t* afull = bars;                  // [kB0ND1]  A operands of a v row written to TMEM (8 transformer warps)
   uint64_t* tfull = bars + 16;             // [2]  conv2 accumulators complete
   uint64_t* tempty = bars + 18;            // [2]  ... drained (8 epilogue warps)
   uint64_t* a1full = bars + 20;            // [kB0NA1]  (3 producer warps)
   uint64_t* a1empty = a1full + kB0NA1;     // [kB0NA1]
   uint64_t* d1full = a1empty + kB0NA1;     // [kB0ND1]  conv1 accumulator complete
-  uint64_t* d1empty = d1full + kB0ND1;     // [kB0ND1]  ... drained (8 transformer warps)
-  uint64_t* dsfull = d1empty + kB0ND1;     // [kB0NDS]
+  uint64_t* dsfull = d1full + 3;           // [kB0NDS]
   uint64_t* dsempty = dsfull + kB0NDS;     // [kB0NDS]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(dsempty + kB0NDS);
   float* s_b1 = reinterpret_cast<float*>(dsempty + kB0NDS + 2);   // [32] conv1 bias, broadcast reads by the transformers
@@ -128,19 +121,15 @@ block0_tc_kernel(const Block0Params p) {
     if (k & 1) v = __ldg(reinterpret_cast<const uint4*>(p.wimg + kB0W2Bytes + kB0B1Bytes + (size_t)((part * 3 + (k >> 1)) * 1024)) + within);
     reinterpret_cast<uint4*>(s_w + 2 * kB0W2Bytes + kB0B1Bytes)[i] = v;
   }
-  // rows 128..135 of a v tile are read (by discarded accumulator rows) but never written: keep them finite
-  for (int i = threadIdx.x; i < p.n_slots * kB0Slab / 16; i += kB0Threads)
-    reinterpret_cast<uint4*>(s_ring)[i] = make_uint4(0, 0, 0, 0);
   if (threadIdx.x < 32) {
     s_b1[threadIdx.x] = __ldg(p.b1 + threadIdx.x);
     s_b2[threadIdx.x] = __ldg(p.b2 + threadIdx.x);
   }
   fence_proxy_async_smem();
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 8; ++i) { mbar_init(&full[i], 8); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < kB0ND1; ++i) { mbar_init(&afull[i], 8); mbar_init(&d1full[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
     for (int i = 0; i < kB0NA1; ++i) { mbar_init(&a1full[i], 3); mbar_init(&a1empty[i], 1); }
-    for (int i = 0; i < kB0ND1; ++i) { mbar_init(&d1full[i], 1); mbar_init(&d1empty[i], 8); }
     for (int i = 0; i < kB0NDS; ++i) { mbar_init(&dsfull[i], 3); mbar_init(&dsempty[i], 1); }
     fence_barrier_init();
   }
@@ -149,8 +138,9 @@ block0_tc_kernel(const Block0Params p) {
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
-  // TMEM: [0,192) conv2 accumulators, column = s*64 + slot*32 + channel; [192,480) D1 ring: three v rows of
-  // 96 columns (phase s at 32*s)
+  // TMEM: [0,192) conv2 accumulators, column = s*64 + slot*32 + channel; [192,512) two v rows of kB0VCols columns:
+  // conv1 accumulator (phase s at 32*s) which the transformers replace IN PLACE by conv2's A operand
+  // [hi k0-15 | lo k0-15 | hi k16-31 | lo k16-31] x 8 columns per phase, then the two lane-shifted copies
   constexpr int D1_COL0 = 192;
   if (warp >= 2 && warp < 10) {            // conv2 accumulators start at zero and return to zero after every drain
     const uint32_t tz = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(((warp - 2) >> 2) * 96);
@@ -168,27 +158,25 @@ block0_tc_kernel(const Block0Params p) {
     // and a single-lane loop pays neither divergence nor __syncwarp per step
     const bool leader = elect_one();
     if (leader) {
-    const uint32_t w_base = smem_u32(s_w), ring_base = smem_u32(s_ring);
+    const uint32_t w_base = smem_u32(s_w);
     const uint32_t a1_base = smem_u32(s_a1), ds_base = smem_u32(s_ds);
     const uint32_t b1_addr = w_base + 2 * kB0W2Bytes, bds_addr = b1_addr + kB0B1Bytes;
     int n1 = 0;                            // conv1 rows issued
-    int slot = 0;
-    uint32_t phase = 0;
-    int g2 = 0, nds = 0;                   // conv2 steps issued (step g starts an output row in slot g & 1)
+    int g2 = 0, nds = 0;                   // conv2 steps issued (step g uses v row g and starts an output row in slot g & 1)
     long long w_a1 = 0, w_d1 = 0, w_vf = 0, w_te = 0, w_ds = 0;
     const long long t_begin = AASIST_CLOCK();
-    const bool coll = (p.collector & 1) != 0;      // conv2 (32 -> 32) MMAs
     const bool coll1 = (p.collector & 2) != 0;     // conv1 / downsample MMAs (K = 16 im2col tiles)
 
-    auto issue_conv1_row = [&]() {         // one v row: all three pool phases in three N=96 MMAs
+    // one v row: all three pool phases in three N=96 MMAs.  It overwrites the TMEM slot of v row n1-2, whose
+    // readers (the conv2 MMAs of that row) were issued earlier by this thread: tcgen05.mma executes in issue order
+    auto issue_conv1_row = [&]() {
       const int ka = n1 % kB0NA1, kd = n1 % kB0ND1;
       AASIST_TIMED_WAIT(&a1full[ka], (n1 / kB0NA1) & 1, w_a1);
-      AASIST_TIMED_WAIT(&d1empty[kd], ((n1 / kB0ND1) & 1) ^ 1, w_d1);
       tc_fence_after_sync();
       {
         const uint32_t a_tile = a1_base + (uint32_t)(ka * kB0A1Stride);
         const uint64_t a_hi = b0_desc_noswz(a_tile, 512), a_lo = b0_desc_noswz(a_tile + 256, 512);   // K slices 0, 1
-        const uint32_t d = tmem_base + (uint32_t)(D1_COL0 + 96 * kd);
+        const uint32_t d = tmem_base + (uint32_t)(D1_COL0 + kB0VCols * kd);
         constexpr uint32_t ID96 = umma_idesc_f16(128, 96);
         if (coll1) {
           umma_f16_keep(d, a_hi, b0_desc_noswz(b1_addr), ID96, 0);            // z_hi * w_hi + bias_hi
@@ -204,37 +192,20 @@ block0_tc_kernel(const Block0Params p) {
       }
       ++n1;
     };
-    // conv2 MMAs of one v tile.  Pool phases that read the same A rows share one wider-N MMA, and so do the
-    // two output rows the tile feeds (tap row dh=1 completes one, dh=0 starts the next): N = 64 / 128 / 192,
-    // everything accumulates (slots are cleared by the epilogue when it drains them) -- block_fused_tc.cu
-    auto mma3 = [&](uint32_t d_tmem, uint32_t a_row, uint32_t w_row, int ntaps) {
+    // conv2 MMAs of one A operand (a pool phase of the v row, or a lane-shifted copy) in TMEM.  Pool phases that
+    // read the same A rows share one wider-N MMA, and so do the two output rows the v row feeds (tap row dh=1
+    // completes one, dh=0 starts the next): N = 64 / 128 / 192, everything accumulates (slots are cleared by the
+    // epilogue when it drains them) -- block_fused_tc.cu
+    auto mma3 = [&](uint32_t d_tmem, uint32_t a_tmem, uint32_t w_row, int ntaps) {
       const uint32_t idesc = ntaps == 3 ? umma_idesc_f16(128, 192)
                                         : (ntaps == 2 ? umma_idesc_f16(128, 128) : umma_idesc_f16(128, 64));
-      const uint64_t a_hi = umma_desc_sw128(a_row), a_lo = umma_desc_sw128(a_row + 64);
       const uint64_t w_hi = umma_desc_sw128(w_row), w_lo = umma_desc_sw128(w_row + 64);
 #pragma unroll
       for (int kc = 0; kc < 2; ++kc) {
-        if (coll) {
-          umma_f16_keep(d_tmem, a_hi + 2 * kc, w_hi + 2 * kc, idesc, 1);
-          umma_f16_reuse(d_tmem, a_hi + 2 * kc, w_lo + 2 * kc, idesc, 1);  // same A: taken from the collector
-          umma_f16(d_tmem, a_lo + 2 * kc, w_hi + 2 * kc, idesc, 1);
-        } else {
-          umma_f16(d_tmem, a_hi + 2 * kc, w_hi + 2 * kc, idesc, 1);
-          umma_f16(d_tmem, a_lo + 2 * kc, w_hi + 2 * kc, idesc, 1);
-          umma_f16(d_tmem, a_hi + 2 * kc, w_lo + 2 * kc, idesc, 1);
-        }
-      }
-    };
-    auto issue_group = [&](uint32_t a_slot, uint32_t wb, int phi) {
-      const uint32_t d0 = tmem_base;
-      if (phi == 1) {
-        mma3(d0, a_slot + 128, wb, 3);
-      } else if (phi == 0) {
-        mma3(d0, a_slot + 128, wb + 8192, 2);
-        mma3(d0 + 128, a_slot + 256, wb, 1);
-      } else {
-        mma3(d0 + 64, a_slot + 128, wb, 2);
-        mma3(d0, a_slot, wb + 16384, 1);
+        const uint32_t a_hi = a_tmem + (uint32_t)(16 * kc), a_lo = a_hi + 8;
+        umma_f16_ts(d_tmem, a_hi, w_hi + 2 * kc, idesc, 1);
+        umma_f16_ts(d_tmem, a_lo, w_hi + 2 * kc, idesc, 1);
+        umma_f16_ts(d_tmem, a_hi, w_lo + 2 * kc, idesc, 1);
       }
     };
 
@@ -245,16 +216,18 @@ block0_tc_kernel(const Block0Params p) {
         // v row r: dh=1 completes output row r-1 (a dummy for r = 0, see block_fused_tc.cu), dh=0 starts row r
         const int g = g2++;
         AASIST_TIMED_WAIT(&tempty[g & 1], (uint32_t)(((g - 1) >> 1) & 1), w_te);
+        AASIST_TIMED_WAIT(&afull[g % kB0ND1], (uint32_t)((g / kB0ND1) & 1), w_vf);
         tc_fence_after_sync();
-        const uint32_t wb = w_base + (uint32_t)((g & 1) * kB0W2Bytes);
-        for (int phi = 0; phi < 3; ++phi) {
-          AASIST_TIMED_WAIT(&full[slot], phase, w_vf);
-          tc_fence_after_sync();
-          {
-            issue_group(ring_base + (uint32_t)slot * kB0Slab, wb, phi);
-            umma_commit(&empty[slot]);
-          }
-            if (++slot == p.n_slots) { slot = 0; phase ^= 1; }
+        {
+          const uint32_t wb = w_base + (uint32_t)((g & 1) * kB0W2Bytes);
+          const uint32_t d0 = tmem_base;
+          const uint32_t av = tmem_base + (uint32_t)(D1_COL0 + kB0VCols * (g % kB0ND1));
+          // tile row m = pooled column j0-1+m of every operand; weight image rows = [tap 2 | tap 1 | tap 0] x 64
+          mma3(d0, av + 32, wb, 3);                    // v phase 1      -> phases 0,1,2 (taps 2,1,0)
+          mma3(d0, av, wb + 8192, 2);                  // v phase 0      -> phases 0,1   (taps 1,0)
+          mma3(d0 + 64, av + 64, wb, 2);               // v phase 2      -> phases 1,2   (taps 2,1)
+          mma3(d0 + 128, av + 128, wb, 1);             // v phase 0 of the next tile row     -> phase 2 (tap 2)
+          mma3(d0, av + 96, wb + 16384, 1);            // v phase 2 of the previous tile row -> phase 0 (tap 0)
         }
         if (r <= 22) {
           // conv_downsample of z row r into the row being started (slot g & 1): K = 16 im2col chunk against
@@ -274,7 +247,7 @@ block0_tc_kernel(const Block0Params p) {
             }
             umma_commit(&dsempty[kq]);
           }
-            ++nds;
+          ++nds;
         }
         umma_commit(&tfull[(g & 1) ^ 1]);
       }
@@ -292,8 +265,8 @@ block0_tc_kernel(const Block0Params p) {
     int tcount = 0;                        // completed conv2 steps (24 per strip; the first is the dummy row -1)
     for (int t = blockIdx.x; t < n_strips; t += gridDim.x) {
       const int jt = t % p.n_jt, b = t / p.n_jt;
-      const int j = jt * kB0Strip + m;
-      const bool store = m < kB0Strip && j / 3 < p.Jn;
+      const int j = jt * kB0Strip + m - 1;                      // tile row m = pooled column j0-1+m
+      const bool store = m >= 1 && m <= kB0Strip && j / 3 < p.Jn;
       const bool valid = j < p.Wo;
       for (int h = -1; h < 23; ++h, ++tcount) {
         const int buf = (tcount & 1) ^ 1;
@@ -327,7 +300,7 @@ block0_tc_kernel(const Block0Params p) {
           float x1 = fmaxf(fmaxf(__uint_as_float(acc[0][2 * i + 1]), __uint_as_float(acc[1][2 * i + 1])),
                            __uint_as_float(acc[2][2 * i + 1])) + bb.y;
           if (!valid) { x0 = 0.f; x1 = 0.f; }
-          b0_split2<false>(x0, x1, hw[i], lw[i]);
+          split2_sat(x0, x1, hw[i], lw[i]);
         }
         __half* o = p.out + ((((size_t)b * 23 + h) * 3 + (j % 3)) * p.Jn + j / 3) * 64 + col0;
         st_global_256(o, hw);
@@ -335,46 +308,39 @@ block0_tc_kernel(const Block0Params p) {
       }
     }
   } else if (warp >= 10 && warp < 18) {
-    // ============ transformers: D1 (TMEM) -> SELU, zero-pad mask, fp16 pairs -> swizzled v tiles ============
-    // warp = (TMEM lane quadrant, 16-channel half).  A whole v row (three phase tiles) is handled at once: one
-    // wait, three tcgen05.ld, the D1 tiles released immediately, 48 SELUs per thread, one proxy fence.
+    // ============ transformers: D1 (TMEM) -> SELU, zero-pad mask, fp16 pairs -> conv2's A operands (TMEM) ============
+    // warp = (TMEM lane quadrant, 16-channel half).  A whole v row is handled at once: one wait, three tcgen05.ld,
+    // 48 SELUs per thread, the pairs stored back over the thread's own 16 accumulator columns of each phase
+    // ([hi | lo] of its K=16 slice), then the two lane-shifted copies: phase 2 of tile row m-1 and phase 0 of tile
+    // row m+1 (shuffles inside the warp; the first / last lane take the neighbouring quadrant's boundary row from a
+    // small shared-memory exchange buffer, double-buffered by row parity: one 128-thread barrier per row and half).
     const int quad = warp & 3, half = (warp - 10) >> 2;
     const int jj = quad * 32 + lane;                             // tile row
     const int col0 = half * 16;
-    const uint32_t row_off = (uint32_t)jj * 128;
-    const uint32_t sw = (uint32_t)(jj & 7);
-    const uint32_t c_hi = (uint32_t)(2 * half), c_lo = (uint32_t)(4 + 2 * half);   // 16-byte chunks of this half
-    int n = 0, slot = 0;
-    uint32_t phase = 0;
+    int n = 0;
     for (int t = blockIdx.x; t < n_strips; t += gridDim.x) {
       const int jt = t % p.n_jt;
       const int j = jt * kB0Strip - 1 + jj;
       // warp-uniform: every row of this warp lies inside [0, W) for all three phases
       const bool valid_all = jt * kB0Strip - 1 + quad * 32 >= 0 && 3 * (jt * kB0Strip - 1 + quad * 32 + 31) + 2 < p.W;
       for (int r = 0; r < 24; ++r, ++n) {
+        const int kd = n % kB0ND1;
+        const uint32_t tslot = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(D1_COL0 + kB0VCols * kd + col0);
         uint32_t acc[3][16];
-        {
-          const int kd = n % kB0ND1;
-          mbar_wait(&d1full[kd], (n / kB0ND1) & 1);
-          tc_fence_after_sync();
+        mbar_wait(&d1full[kd], (n / kB0ND1) & 1);
+        tc_fence_after_sync();
 #pragma unroll
-          for (int s = 0; s < 3; ++s)
-            tmem_ld16_async(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(D1_COL0 + 96 * kd + 32 * s + col0),
-                            acc[s]);
+        for (int s = 0; s < 3; ++s) tmem_ld16_async(tslot + (uint32_t)(32 * s), acc[s]);
 #pragma unroll
-          for (int s = 0; s < 3; ++s) tmem_ld_wait16(acc[s]);
-          tc_fence_before_sync();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&d1empty[kd]);
-        }
-        int sl[3];
+        for (int s = 0; s < 3; ++s) tmem_ld_wait16(acc[s]);
+        // acc[s] <- [hi words (8) | lo words (8)] of phase s, in place
 #pragma unroll
         for (int s = 0; s < 3; ++s) {
           uint32_t hw[8], lw[8];
           if (valid_all) {                                       // interior strip: no zero-padding mask needed
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              b0_split2<true>(b0_selu_scaled(__uint_as_float(acc[s][2 * i])),
+              split2_sat(b0_selu_scaled(__uint_as_float(acc[s][2 * i])),
                               b0_selu_scaled(__uint_as_float(acc[s][2 * i + 1])), hw[i], lw[i]);
           } else {
             const bool valid = j >= 0 && 3 * j + s < p.W;        // conv2 zero-pads v itself
@@ -383,24 +349,52 @@ block0_tc_kernel(const Block0Params p) {
               float x0 = b0_selu_scaled(__uint_as_float(acc[s][2 * i]));
               float x1 = b0_selu_scaled(__uint_as_float(acc[s][2 * i + 1]));
               if (!valid) { x0 = 0.f; x1 = 0.f; }
-              b0_split2<true>(x0, x1, hw[i], lw[i]);
+              split2_sat(x0, x1, hw[i], lw[i]);
             }
           }
-          mbar_wait(&empty[slot], phase ^ 1);
-          uint8_t* row = s_ring + (size_t)slot * kB0Slab + row_off;
-          *reinterpret_cast<uint4*>(row + ((c_hi ^ sw) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-          *reinterpret_cast<uint4*>(row + (((c_hi + 1) ^ sw) << 4)) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
-          *reinterpret_cast<uint4*>(row + ((c_lo ^ sw) << 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-          *reinterpret_cast<uint4*>(row + (((c_lo + 1) ^ sw) << 4)) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
-          sl[s] = slot;
-          if (++slot == p.n_slots) { slot = 0; phase ^= 1; }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { acc[s][i] = hw[i]; acc[s][8 + i] = lw[i]; }
+          tmem_st16(tslot + (uint32_t)(32 * s), acc[s]);
         }
-        fence_proxy_async_smem();
-        __syncwarp();
+        // boundary rows for the neighbouring quadrants: kind 0 = phase 2 of this warp's last row, 1 = phase 0 of its first
+        uint32_t* xw = s_xch + (((n & 1) * 2 + half) * 4 + quad) * 32;
+        if (lane == 31) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            reinterpret_cast<uint4*>(xw)[i] = make_uint4(acc[2][4 * i], acc[2][4 * i + 1], acc[2][4 * i + 2], acc[2][4 * i + 3]);
+        }
         if (lane == 0) {
 #pragma unroll
-          for (int s = 0; s < 3; ++s) mbar_arrive(&full[sl[s]]);
+          for (int i = 0; i < 4; ++i)
+            reinterpret_cast<uint4*>(xw + 16)[i] = make_uint4(acc[0][4 * i], acc[0][4 * i + 1], acc[0][4 * i + 2], acc[0][4 * i + 3]);
         }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          acc[2][i] = __shfl_up_sync(0xffffffffu, acc[2][i], 1);      // phase 2 of tile row m-1
+          acc[0][i] = __shfl_down_sync(0xffffffffu, acc[0][i], 1);    // phase 0 of tile row m+1
+        }
+        if (half) asm volatile("bar.sync 5, 128;" ::: "memory");
+        else asm volatile("bar.sync 4, 128;" ::: "memory");
+        if (lane == 0 && quad > 0) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 v = reinterpret_cast<const uint4*>(xw - 32)[i];
+            acc[2][4 * i] = v.x; acc[2][4 * i + 1] = v.y; acc[2][4 * i + 2] = v.z; acc[2][4 * i + 3] = v.w;
+          }
+        }
+        if (lane == 31 && quad < 3) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 v = reinterpret_cast<const uint4*>(xw + 32 + 16)[i];
+            acc[0][4 * i] = v.x; acc[0][4 * i + 1] = v.y; acc[0][4 * i + 2] = v.z; acc[0][4 * i + 3] = v.w;
+          }
+        }
+        tmem_st16(tslot + 96u, acc[2]);
+        tmem_st16(tslot + 128u, acc[0]);
+        tmem_st_wait();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&afull[kd]);
       }
     }
   } else if (warp >= 18 || warp == 0) {
@@ -436,7 +430,7 @@ block0_tc_kernel(const Block0Params p) {
       };
       // One pass builds everything that depends on z rows q-1 ("up") and q ("dn"): the conv1 im2col tile of v row q
       // (tile row jj: window columns 3jj .. 3jj+4 of both rows serve all three pool phases) and the
-      // conv_downsample tile of output row q-1 (row m = jj-1: the same five columns of the up row).
+      // conv_downsample tile of output row q-1 (the same tile row: the same five columns of the up row).
       // A thread reads the five (hi,lo) words of each row once and permutes them into the operand rows
       //   conv1 (K=32): [up_hi(5) dn_hi(5) 1 0(5) | up_lo(5) dn_lo(5) 0(6)]    downsample (K=16): [z_hi(5) z_lo(5) 0(6)]
       auto row_pass = [&](int q) {
@@ -452,7 +446,7 @@ block0_tc_kernel(const Block0Params p) {
         }
         const uint32_t* zu = s_z + ((q - 1 + 3) % 3) * kB0ZW;
         const uint32_t* zd = s_z + (q % 3) * kB0ZW;
-        for (int jj = ptid; jj < 129; jj += 96) {
+        for (int jj = ptid; jj < 128; jj += 96) {
           uint32_t U[5], D[5];
 #pragma unroll
           for (int i = 0; i < 5; ++i) {
@@ -461,7 +455,7 @@ block0_tc_kernel(const Block0Params p) {
           }
           auto hh = [](uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x5410); };   // (a.hi, b.hi)
           auto ll = [](uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x7632); };   // (a.lo, b.lo)
-          if (jj < 128) {
+          {
             // K = 32 row: [up_hi(5) dn_hi(5) 1 0(5) | up_lo(5) dn_lo(5) 0(6)] as four 16-byte K-groups
             uint8_t* row = dst + (jj >> 3) * 512 + (jj & 7) * 16;
             *reinterpret_cast<uint4*>(row) = make_uint4(hh(U[0], U[1]), hh(U[2], U[3]), hh(U[4], D[0]), hh(D[1], D[2]));
@@ -469,9 +463,8 @@ block0_tc_kernel(const Block0Params p) {
             *reinterpret_cast<uint4*>(row + 256) = make_uint4(ll(U[0], U[1]), ll(U[2], U[3]), ll(U[4], D[0]), ll(D[1], D[2]));
             *reinterpret_cast<uint4*>(row + 384) = make_uint4(ll(D[3], D[4]), 0u, 0u, 0u);
           }
-          if (up && jj >= 1) {
-            const int m = jj - 1;
-            uint8_t* row = dds + (m >> 3) * 256 + (m & 7) * 16;
+          if (up) {
+            uint8_t* row = dds + (jj >> 3) * 256 + (jj & 7) * 16;
             *reinterpret_cast<uint4*>(row) = make_uint4(hh(U[0], U[1]), hh(U[2], U[3]),
                                                         __byte_perm(U[4], U[0], 0x7610), ll(U[1], U[2]));
             *reinterpret_cast<uint4*>(row + 128) = make_uint4(ll(U[3], U[4]), 0u, 0u, 0u);
@@ -566,13 +559,8 @@ int launch_block0_tc(aasist_handle* h, int sm_count, const uint8_t* wimg, const 
   p.z = z; p.out = out; p.wimg = wimg; p.b1 = b1; p.b2 = b2;
   p.B = nb; p.W = W; p.J = (W + 2) / 3; p.Wo = W / 3; p.Jn = (p.Wo + 2) / 3;
   p.n_jt = (std::max(p.J, 3 * p.Jn) + kB0Strip - 1) / kB0Strip;
-  const int fixed = 1024 + kB0SmemImgBytes + kB0NA1 * kB0A1Stride + kB0NDS * kB0DsBytes + 6 * kB0ZW * 2 + 1024;
-  p.n_slots = std::min(8, (227 * 1024 - fixed) / kB0Slab);
-  if (p.n_slots < 4) {
-    set_error("block0_tc: shared memory budget allows only %d ring slots", p.n_slots);
-    return AASIST_E_INVALID;
-  }
-  const size_t smem = (size_t)fixed + (size_t)p.n_slots * kB0Slab;
+  const size_t smem = 1024 + kB0SmemImgBytes + kB0NA1 * kB0A1Stride + kB0NDS * kB0DsBytes + 6 * kB0ZW * 2 +
+                      kB0XchWords * 4 + 1024;
   AASIST_CUDA(cudaFuncSetAttribute(block0_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = std::min(nb * p.n_jt, sm_count);
   static int want_stats = -1;
@@ -599,7 +587,7 @@ int launch_block0_tc(aasist_handle* h, int sm_count, const uint8_t* wimg, const 
     for (int c = 0; c < grid; ++c)
       for (int k = 0; k < 6; ++k) acc[k] += (double)hst[(size_t)c * 8 + k] / grid;
     const double rows = (double)nb * p.n_jt * 23 / grid;
-    fprintf(stderr, "[block0 stats] per row-tile cycles: total %.0f | wait a1full %.0f d1empty %.0f vfull %.0f tempty %.0f "
+    fprintf(stderr, "[block0 stats] per row-tile cycles: total %.0f | wait a1full %.0f - %.0f afull %.0f tempty %.0f "
             "dsfull %.0f | issuing %.0f\n", acc[0] / rows, acc[1] / rows, acc[2] / rows, acc[3] / rows, acc[4] / rows,
             acc[5] / rows, (acc[0] - acc[1] - acc[2] - acc[3] - acc[4] - acc[5]) / rows);
     cudaFree(p.stats);

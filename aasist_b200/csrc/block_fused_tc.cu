@@ -64,20 +64,6 @@ __device__ __forceinline__ float bf_selu_scaled(float y) {
   const float n = fminf(fmaf(e, kSeluScale * kSeluAlpha, -(kSeluScale * kSeluAlpha)), 0.f);
   return fmaf(fmaxf(y, 0.f), kSeluScale * 0.6931471805599453f, n);
 }
-template <bool LOWER_BOUNDED>
-__device__ __forceinline__ void bf_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  a = fminf(a, 65504.f);
-  b = fminf(b, 65504.f);
-  if (!LOWER_BOUNDED) {
-    a = fmaxf(a, -65504.f);
-    b = fmaxf(b, -65504.f);
-  }
-  const __half2 h = __floats2half2_rn(a, b);
-  const float2 f = __half22float2(h);
-  const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
-}
 
 __global__ void __launch_bounds__(kBfThreads, 1)
 block_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const BlockFusedParams p) {
@@ -339,7 +325,7 @@ block_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const BlockFusedP
           } else if (j / 3 < p.Jn) {
             uint32_t hw[8], lw[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) bf_split2<false>(mx[2 * i], mx[2 * i + 1], hw[i], lw[i]);
+            for (int i = 0; i < 8; ++i) split2_sat(mx[2 * i], mx[2 * i + 1], hw[i], lw[i]);
             __half* o = p.out + ((((size_t)b * 23 + h) * 3 + (j % 3)) * p.Jn + j / 3) * 64 + col0;
             st_global_256(o, hw);
             st_global_256(o + 32, lw);
@@ -417,7 +403,7 @@ block_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const BlockFusedP
           if (valid_all) {                                         // interior strip: no zero-padding mask needed
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              bf_split2<true>(bf_selu_scaled(__uint_as_float(acc[s][2 * i])),
+              split2_sat(bf_selu_scaled(__uint_as_float(acc[s][2 * i])),
                               bf_selu_scaled(__uint_as_float(acc[s][2 * i + 1])), hw[i], lw[i]);
           } else {
             const bool valid = j >= 0 && 3 * j + s < p.W;          // conv2 zero-pads v itself
@@ -426,7 +412,7 @@ block_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const BlockFusedP
               float x0 = bf_selu_scaled(__uint_as_float(acc[s][2 * i]));
               float x1 = bf_selu_scaled(__uint_as_float(acc[s][2 * i + 1]));
               if (!valid) { x0 = 0.f; x1 = 0.f; }
-              bf_split2<true>(x0, x1, hw[i], lw[i]);
+              split2_sat(x0, x1, hw[i], lw[i]);
             }
           }
           mbar_wait(&vempty[slot], phase ^ 1);

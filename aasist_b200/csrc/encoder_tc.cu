@@ -103,21 +103,11 @@ __device__ __forceinline__ float selu_scaled(float y) {
   return fmaf(fmaxf(y, 0.f), kSeluScale * 0.6931471805599453f, n);
 }
 
-// (a,b) fp32 -> packed hi half2 and lo half2 (a ~= hi+lo to 2^-22), saturating at the fp16 range.
-// LOWER_BOUNDED: the values are SELU outputs (>= -1.76), only the upper clamp is needed.
+// (a,b) fp32 -> packed hi half2 and lo half2 (a ~= hi+lo to 2^-22), saturating at the fp16 range inside the
+// conversion instruction (ptx.cuh split2_sat)
 template <bool LOWER_BOUNDED = false>
 __device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  a = fminf(a, 65504.f);
-  b = fminf(b, 65504.f);
-  if (!LOWER_BOUNDED) {
-    a = fmaxf(a, -65504.f);
-    b = fmaxf(b, -65504.f);
-  }
-  const __half2 h = __floats2half2_rn(a, b);
-  const float2 f = __half22float2(h);
-  const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
+  split2_sat(a, b, hi, lo);
 }
 // store 16 fp32 channels as hi (32 B) and lo (32 B) fp16 vectors
 template <bool LOWER_BOUNDED = false>

@@ -172,6 +172,19 @@ __device__ __forceinline__ void umma_f16_reuse(uint32_t d, uint64_t a, uint64_t 
   umma_f16(d, a, b, i, acc);
 }
 #endif
+// D[tmem] (+)= A[TMEM] * B[smem]: the A operand is read from tensor memory (lane = row m, 32-bit column c of the
+// K=16 slice holds elements k = 2c, 2c+1: 8 columns per slice) -- no shared-memory A fetch at all.  Used where the A
+// operand is produced on chip from another accumulator (conv1 -> conv2 of the fused blocks).
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive on an mbarrier once every MMA issued so far by this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -232,6 +245,13 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+// store 8 registers to 32 lanes x 8 consecutive columns (asynchronous until tmem_st_wait)
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
@@ -279,6 +299,18 @@ __device__ __forceinline__ void ld_global_nc_256(const void* p, uint32_t (&w)[8]
 __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
   hi = __float2half_rn(v);
   lo = __float2half_rn(v - __half2float(hi));
+}
+// two fp32 values -> packed fp16 pairs: hi = rn(a,b) saturated to +-65504 by the conversion itself
+// (F2FP.SATFINITE: no separate clamps), lo = rn(v - hi); the low half of each word is `a`
+__device__ __forceinline__ uint32_t cvt_f16x2_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ void split2_sat(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = cvt_f16x2_sat(a, b);
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  lo = cvt_f16x2_sat(a - f.x, b - f.y);
 }
 __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
   return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
