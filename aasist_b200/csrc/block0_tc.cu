@@ -13,13 +13,15 @@
 // operand NEVER LEAVES TENSOR MEMORY: tcgen05.ld -> SELU -> zero outside [0,W) -> fp16 hi/lo -> tcgen05.st back
 // into the same columns (an fp32 accumulator and its fp16 pair are the same 4 bytes), and conv2 issues
 // tcgen05.mma with the A operand in TMEM (lane = tile row, 8 columns per K=16 slice).  The two taps that read
-// the neighbouring tile row (phase 2 one row up, phase 0 one row down) get their own lane-shifted copies
-// (warp shuffles + a 2 KB exchange buffer for the four quadrant boundaries).  conv2's MMAs therefore fetch only
+// the neighbouring tile row (phase 2 one row up, phase 0 one row down) get their own lane-shifted copies (warp
+// shuffles; each 32-lane quadrant of the tile carries its own halo rows, so nothing crosses a warp -- shared
+// memory round trips cost 150-250 cycles under the MMAs' operand traffic).  conv2's MMAs therefore fetch only
 // their weights from shared memory: no v tiles are written to or read from it (they were 170 KB of the 330 KB
 // of shared-memory traffic per row-tile that bounded this kernel).  Otherwise conv2 runs like conv_tc_kernel
 // (strip-mined, two output rows in flight, phase-split pooling), and conv_downsample (1 -> 32 channels,
 // 3 taps) is two more K=16 MMAs per output row on a second im2col tile.
-// Work item: (utterance, strip of 126 pooled columns): tile row m = pooled column j0-1+m, rows 1..126 are stored.
+// Work item: (utterance, strip of 120 pooled columns): tile row m = pooled column j0 + 30*(m/32) + m%32 - 1; rows
+// 1..30 of every quadrant are stored.
 //
 // warps: 0 idle | 1 MMA issuer + TMEM owner | 2-9 epilogue | 10-17 transformers | 18-19 im2col producers
 #include <stdio.h>
@@ -33,13 +35,14 @@ namespace aasist {
 
 using namespace ptx;
 
-constexpr int kB0Strip = 126;               // valid pooled columns per strip
+constexpr int kB0Strip = 120;               // valid pooled columns per strip: every 32-row TMEM lane quadrant carries its own
+                                            // halo rows (tile row jj = pooled column j0 + 30*(jj/32) + jj%32 - 1, rows 1..30 of a
+                                            // quadrant are stored), so the lane-shifted operand copies never cross a warp
 constexpr int kB0A1Stride = 16 * 512;       // conv1 im2col tile of one v row: 128 rows x 64 B (K = 32), no-swizzle
                                             // canonical: 8-row groups of 512 B = 4 K-groups x (8 rows x 16 B)
 constexpr int kB0DsBytes = 16 * 256;        // downsample im2col tile: 128 rows x 32 B
 constexpr int kB0NA1 = 3, kB0ND1 = 2, kB0NDS = 3;   // rings of v rows (im2col tiles, D1 / A-operand slots in TMEM), downsample tiles
 constexpr int kB0VCols = 160;               // TMEM columns of one v row: D1 = A(phase 0,1,2) in place [0,96), A(phase 2, row-1) [96,128), A(phase 0, row+1) [128,160)
-constexpr int kB0XchWords = 2 * 2 * 4 * 2 * 16;   // boundary exchange [parity][half][quadrant][kind][16 words]
 constexpr int kB0Threads = 640;
 constexpr int kB0ZW = 400;                  // z columns kept per row: 3*j0-4 .. 3*j0+395 (392 used)
 constexpr int kB0W2Bytes = 6 * 32 * 128;    // conv2 weight image (6 taps x [32 rows x 128 B])
@@ -88,8 +91,7 @@ block0_tc_kernel(const Block0Params p) {
   uint8_t* s_a1 = smem + kB0SmemImgBytes;                      // conv1 im2col ring
   uint8_t* s_ds = s_a1 + kB0NA1 * kB0A1Stride;                 // downsample im2col ring
   uint32_t* s_z = reinterpret_cast<uint32_t*>(s_ds + kB0NDS * kB0DsBytes);   // [3][kB0ZW] rolling rows of z as (hi,lo) fp16 words
-  uint32_t* s_xch = s_z + 3 * kB0ZW;       // transformer boundary rows (kB0XchWords)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_xch + kB0XchWords);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_z + 3 * kB0ZW);
   uint64_t* afull = bars;                  // [kB0ND1]  A operands of a v row written to TMEM (8 transformer warps)
   uint64_t* tfull = bars + 16;             // [2]  conv2 accumulators complete
   uint64_t* tempty = bars + 18;            // [2]  ... drained (8 epilogue warps)
@@ -253,7 +255,7 @@ block0_tc_kernel(const Block0Params p) {
       }
     }
     if (p.stats) {
-      long long* st = p.stats + (size_t)blockIdx.x * 8;
+      long long* st = p.stats + (size_t)blockIdx.x * 16;
       st[0] = AASIST_CLOCK() - t_begin; st[1] = w_a1; st[2] = w_d1; st[3] = w_vf; st[4] = w_te; st[5] = w_ds;
     }
     }
@@ -265,8 +267,8 @@ block0_tc_kernel(const Block0Params p) {
     int tcount = 0;                        // completed conv2 steps (24 per strip; the first is the dummy row -1)
     for (int t = blockIdx.x; t < n_strips; t += gridDim.x) {
       const int jt = t % p.n_jt, b = t / p.n_jt;
-      const int j = jt * kB0Strip + m - 1;                      // tile row m = pooled column j0-1+m
-      const bool store = m >= 1 && m <= kB0Strip && j / 3 < p.Jn;
+      const int j = jt * kB0Strip + 30 * quad + lane - 1;       // tile row m -> pooled column
+      const bool store = lane >= 1 && lane <= 30 && j / 3 < p.Jn;
       const bool valid = j < p.Wo;
       for (int h = -1; h < 23; ++h, ++tcount) {
         const int buf = (tcount & 1) ^ 1;
@@ -312,27 +314,31 @@ block0_tc_kernel(const Block0Params p) {
     // warp = (TMEM lane quadrant, 16-channel half).  A whole v row is handled at once: one wait, three tcgen05.ld,
     // 48 SELUs per thread, the pairs stored back over the thread's own 16 accumulator columns of each phase
     // ([hi | lo] of its K=16 slice), then the two lane-shifted copies: phase 2 of tile row m-1 and phase 0 of tile
-    // row m+1 (shuffles inside the warp; the first / last lane take the neighbouring quadrant's boundary row from a
-    // small shared-memory exchange buffer, double-buffered by row parity: one 128-thread barrier per row and half).
+    // row m+1 (shuffles inside the warp: the first and last lane of a quadrant are halo rows whose results are
+    // discarded).
     const int quad = warp & 3, half = (warp - 10) >> 2;
     const int jj = quad * 32 + lane;                             // tile row
     const int col0 = half * 16;
     int n = 0;
+    long long x_wait = 0, x_ld = 0, x_math = 0, x_shift = 0, x_shfl = 0, x_bar = 0, x_fix = 0, x_stw = 0;   // stats build: where a transformer warp spends a row
     for (int t = blockIdx.x; t < n_strips; t += gridDim.x) {
       const int jt = t % p.n_jt;
-      const int j = jt * kB0Strip - 1 + jj;
+      const int j = jt * kB0Strip + 30 * quad + lane - 1;
       // warp-uniform: every row of this warp lies inside [0, W) for all three phases
-      const bool valid_all = jt * kB0Strip - 1 + quad * 32 >= 0 && 3 * (jt * kB0Strip - 1 + quad * 32 + 31) + 2 < p.W;
+      const bool valid_all = jt * kB0Strip + 30 * quad - 1 >= 0 && 3 * (jt * kB0Strip + 30 * quad + 30) + 2 < p.W;
       for (int r = 0; r < 24; ++r, ++n) {
         const int kd = n % kB0ND1;
         const uint32_t tslot = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(D1_COL0 + kB0VCols * kd + col0);
         uint32_t acc[3][16];
+        const long long c0 = AASIST_CLOCK();
         mbar_wait(&d1full[kd], (n / kB0ND1) & 1);
         tc_fence_after_sync();
+        const long long c1 = AASIST_CLOCK();
 #pragma unroll
         for (int s = 0; s < 3; ++s) tmem_ld16_async(tslot + (uint32_t)(32 * s), acc[s]);
 #pragma unroll
         for (int s = 0; s < 3; ++s) tmem_ld_wait16(acc[s]);
+        const long long c2 = AASIST_CLOCK();
         // acc[s] <- [hi words (8) | lo words (8)] of phase s, in place
 #pragma unroll
         for (int s = 0; s < 3; ++s) {
@@ -356,46 +362,33 @@ block0_tc_kernel(const Block0Params p) {
           for (int i = 0; i < 8; ++i) { acc[s][i] = hw[i]; acc[s][8 + i] = lw[i]; }
           tmem_st16(tslot + (uint32_t)(32 * s), acc[s]);
         }
-        // boundary rows for the neighbouring quadrants: kind 0 = phase 2 of this warp's last row, 1 = phase 0 of its first
-        uint32_t* xw = s_xch + (((n & 1) * 2 + half) * 4 + quad) * 32;
-        if (lane == 31) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            reinterpret_cast<uint4*>(xw)[i] = make_uint4(acc[2][4 * i], acc[2][4 * i + 1], acc[2][4 * i + 2], acc[2][4 * i + 3]);
-        }
-        if (lane == 0) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            reinterpret_cast<uint4*>(xw + 16)[i] = make_uint4(acc[0][4 * i], acc[0][4 * i + 1], acc[0][4 * i + 2], acc[0][4 * i + 3]);
-        }
+#ifdef B0_EXP_STWAIT
+        tmem_st_wait();
+#endif
+        const long long c3 = AASIST_CLOCK();
+        const long long c3a = AASIST_CLOCK();
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          acc[2][i] = __shfl_up_sync(0xffffffffu, acc[2][i], 1);      // phase 2 of tile row m-1
+          acc[2][i] = __shfl_up_sync(0xffffffffu, acc[2][i], 1);      // phase 2 of tile row m-1 (lane 0: a halo row, unused)
           acc[0][i] = __shfl_down_sync(0xffffffffu, acc[0][i], 1);    // phase 0 of tile row m+1
         }
-        if (half) asm volatile("bar.sync 5, 128;" ::: "memory");
-        else asm volatile("bar.sync 4, 128;" ::: "memory");
-        if (lane == 0 && quad > 0) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint4 v = reinterpret_cast<const uint4*>(xw - 32)[i];
-            acc[2][4 * i] = v.x; acc[2][4 * i + 1] = v.y; acc[2][4 * i + 2] = v.z; acc[2][4 * i + 3] = v.w;
-          }
-        }
-        if (lane == 31 && quad < 3) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint4 v = reinterpret_cast<const uint4*>(xw + 32 + 16)[i];
-            acc[0][4 * i] = v.x; acc[0][4 * i + 1] = v.y; acc[0][4 * i + 2] = v.z; acc[0][4 * i + 3] = v.w;
-          }
-        }
+        const long long c4 = AASIST_CLOCK(), c5 = c4;
+        const long long c5a = AASIST_CLOCK();
         tmem_st16(tslot + 96u, acc[2]);
         tmem_st16(tslot + 128u, acc[0]);
+        const long long c6 = AASIST_CLOCK();
         tmem_st_wait();
+        const long long c7 = AASIST_CLOCK();
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&afull[kd]);
+        x_wait += c1 - c0; x_ld += c2 - c1; x_math += c3 - c2; x_shift += AASIST_CLOCK() - c3;
+        x_shfl += c4 - c3a; x_bar += c3a - c3; x_fix += c5a - c5; x_stw += c6 - c5a;
       }
+    }
+    if (p.stats && warp == 10 && lane == 0) {
+      long long* st = p.stats + (size_t)blockIdx.x * 16 + 8;
+      st[0] = x_wait; st[1] = x_ld; st[2] = x_math; st[3] = x_shift; st[4] = x_shfl; st[5] = x_bar; st[6] = x_fix; st[7] = x_stw;
     }
   } else if (warp >= 18 || warp == 0) {
     // ============ im2col producers (warps 0, 18, 19): z taps as fp16 pairs, one 32-byte row per tile row ============
@@ -429,7 +422,7 @@ block0_tc_kernel(const Block0Params p) {
         }
       };
       // One pass builds everything that depends on z rows q-1 ("up") and q ("dn"): the conv1 im2col tile of v row q
-      // (tile row jj: window columns 3jj .. 3jj+4 of both rows serve all three pool phases) and the
+      // (tile row jj: five window columns of both rows serve all three pool phases) and the
       // conv_downsample tile of output row q-1 (the same tile row: the same five columns of the up row).
       // A thread reads the five (hi,lo) words of each row once and permutes them into the operand rows
       //   conv1 (K=32): [up_hi(5) dn_hi(5) 1 0(5) | up_lo(5) dn_lo(5) 0(6)]    downsample (K=16): [z_hi(5) z_lo(5) 0(6)]
@@ -449,9 +442,11 @@ block0_tc_kernel(const Block0Params p) {
         for (int jj = ptid; jj < 128; jj += 96) {
           uint32_t U[5], D[5];
 #pragma unroll
+          const int wc = 3 * (jj - 2 * (jj >> 5));               // tile row jj = pooled column j0 - 1 + jj - 2*(jj/32)
+#pragma unroll
           for (int i = 0; i < 5; ++i) {
-            U[i] = up ? zu[3 * jj + i] : 0u;
-            D[i] = dn ? zd[3 * jj + i] : 0u;
+            U[i] = up ? zu[wc + i] : 0u;
+            D[i] = dn ? zd[wc + i] : 0u;
           }
           auto hh = [](uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x5410); };   // (a.hi, b.hi)
           auto ll = [](uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x7632); };   // (a.lo, b.lo)
@@ -560,7 +555,7 @@ int launch_block0_tc(aasist_handle* h, int sm_count, const uint8_t* wimg, const 
   p.B = nb; p.W = W; p.J = (W + 2) / 3; p.Wo = W / 3; p.Jn = (p.Wo + 2) / 3;
   p.n_jt = (std::max(p.J, 3 * p.Jn) + kB0Strip - 1) / kB0Strip;
   const size_t smem = 1024 + kB0SmemImgBytes + kB0NA1 * kB0A1Stride + kB0NDS * kB0DsBytes + 6 * kB0ZW * 2 +
-                      kB0XchWords * 4 + 1024;
+                      1024;
   AASIST_CUDA(cudaFuncSetAttribute(block0_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = std::min(nb * p.n_jt, sm_count);
   static int want_stats = -1;
@@ -571,8 +566,8 @@ int launch_block0_tc(aasist_handle* h, int sm_count, const uint8_t* wimg, const 
   p.stats = nullptr;
   p.collector = ((collector_mask() >> 1) & 1) | (((collector_mask() >> 5) & 1) << 1);
   if (want_stats) {
-    AASIST_CUDA(cudaMalloc(&p.stats, sizeof(long long) * 8 * grid));
-    AASIST_CUDA(cudaMemset(p.stats, 0, sizeof(long long) * 8 * grid));
+    AASIST_CUDA(cudaMalloc(&p.stats, sizeof(long long) * 16 * grid));
+    AASIST_CUDA(cudaMemset(p.stats, 0, sizeof(long long) * 16 * grid));
   }
   {
     LaunchSpan span(h, "enc0.fused_conv1_conv2_tc", st);
@@ -580,16 +575,18 @@ int launch_block0_tc(aasist_handle* h, int sm_count, const uint8_t* wimg, const 
   }
   AASIST_CUDA(cudaGetLastError());
   if (want_stats) {   // debugging aid: where the MMA warp waits (cycles, mean over CTAs)
-    std::vector<long long> hst((size_t)8 * grid);
+    std::vector<long long> hst((size_t)16 * grid);
     AASIST_CUDA(cudaStreamSynchronize(st));
     AASIST_CUDA(cudaMemcpy(hst.data(), p.stats, sizeof(long long) * hst.size(), cudaMemcpyDeviceToHost));
-    double acc[6] = {0, 0, 0, 0, 0, 0};
+    double acc[16] = {0};
     for (int c = 0; c < grid; ++c)
-      for (int k = 0; k < 6; ++k) acc[k] += (double)hst[(size_t)c * 8 + k] / grid;
+      for (int k = 0; k < 16; ++k) acc[k] += (double)hst[(size_t)c * 16 + k] / grid;
     const double rows = (double)nb * p.n_jt * 23 / grid;
     fprintf(stderr, "[block0 stats] per row-tile cycles: total %.0f | wait a1full %.0f - %.0f afull %.0f tempty %.0f "
-            "dsfull %.0f | issuing %.0f\n", acc[0] / rows, acc[1] / rows, acc[2] / rows, acc[3] / rows, acc[4] / rows,
-            acc[5] / rows, (acc[0] - acc[1] - acc[2] - acc[3] - acc[4] - acc[5]) / rows);
+            "dsfull %.0f | issuing %.0f || transformer warp: wait d1full %.0f, tcgen05.ld %.0f, selu+split+st %.0f, "
+            "shifted copies %.0f (shfl %.0f, xch writes %.0f, fix %.0f, 2 x tcgen05.st issue %.0f)\n", acc[0] / rows, acc[1] / rows, acc[2] / rows, acc[3] / rows, acc[4] / rows,
+            acc[5] / rows, (acc[0] - acc[1] - acc[2] - acc[3] - acc[4] - acc[5]) / rows, acc[8] / rows, acc[9] / rows,
+            acc[10] / rows, acc[11] / rows, acc[12] / rows, acc[13] / rows, acc[14] / rows, acc[15] / rows);
     cudaFree(p.stats);
   }
   return 0;
