@@ -6,6 +6,9 @@
 //   a8  HtrgGraphAttentionLayer         models/AASIST.py:150-282
 //   a9  branch fusion, readout, head    models/AASIST.py:865-921
 //   a11 RawGAT-ST graph tail            models/RawNetGatSpoofST.py:338-356
+#include <stdio.h>
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -27,6 +30,13 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+#ifdef AASIST_KERNEL_STATS
+__device__ long long g_graph_stats[32];
+#define LSTAMP(k) do { if (threadIdx.x == 0) { long long now_ = clock64(); atomicAdd((unsigned long long*)&g_graph_stats[k], (unsigned long long)(now_ - *S.tlast)); *S.tlast = now_; } } while (0)
+#else
+#define LSTAMP(k) do { } while (0)
+#endif
+
 struct Scratch {
   float* Wst;    // [kMaxDim][kMaxDim] staged attention projection (transposed, padded to Dop).  ALIASES the layer
                  // output buffer and AGG (carve_layer_buffers): neither is live while the attention map is built,
@@ -42,6 +52,7 @@ struct Scratch {
   float* wts;    // [nmax] pool weights (pre-sigmoid) / master logits
   int* idx;      // [nmax]
   float* aggM;   // [kMaxDim]
+  long long* tlast;   // stats build only: time of the previous stamp (thread 0)
 };
 
 // ---- attention logits over all unordered node pairs (the map is symmetric) --------------
@@ -176,10 +187,15 @@ __device__ void linear_rows(const float* IN, const float* IN2, int n, int ldin, 
 // GraphAttentionLayer.forward (AASIST.py:43-59): X (N,D) -> OUT (N,Do)
 __device__ void gat_layer(const float* X, int N, int ld, const GatParams& P, float* OUT,
                           const Scratch& S) {
+  LSTAMP(12);
   att_logits(X, N, ld, P.D, P.Do, P.attWt, P.attB, P.attW, P.attW, P.attW, N, P.temp, S);
+  LSTAMP(13);
   softmax_rows(N, S);
+  LSTAMP(14);
   aggregate(X, N, ld, P.D, S);
+  LSTAMP(15);
   linear_rows<true>(S.AGG, X, N, ld, P.D, P.pWt, P.qWt, P.bias, P.Do, OUT, ld);
+  LSTAMP(16);
 }
 
 // HtrgGraphAttentionLayer.forward (AASIST.py:150-185).
@@ -189,10 +205,14 @@ __device__ void htrg_layer(const float* X1, int n1, const float* X2, int n2, int
                            const float* m_in, const HtrgParams& P, float* HX, float* OUT,
                            float* m_out, const Scratch& S) {
   const int N = n1 + n2, D = P.D, Do = P.Do;
+  LSTAMP(12);
   linear_rows<false>(X1, nullptr, n1, ld, D, P.t1Wt, nullptr, P.t1B, D, HX, ld);              // :158
   linear_rows<false>(X2, nullptr, n2, ld, D, P.t2Wt, nullptr, P.t2B, D, HX + n1 * ld, ld);    // :159
+  LSTAMP(17);
   att_logits(HX, N, ld, D, Do, P.attWt, P.attB, P.w11, P.w22, P.w12, n1, P.temp, S);          // :225-251
+  LSTAMP(18);
   softmax_rows(N, S);                                                                        // :253
+  LSTAMP(19);
   // master attention (AASIST.py:208-223): lm[j] = wM . tanh(W_M (x_j * m) + b_M) / temp
   {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -238,8 +258,11 @@ __device__ void htrg_layer(const float* X1, int n1, const float* X2, int n2, int
     }
     __syncthreads();
   }
+  LSTAMP(20);
   aggregate(HX, N, ld, D, S);                                                                 // :258
+  LSTAMP(21);
   linear_rows<true>(S.AGG, HX, N, ld, D, P.pWt, P.qWt, P.bias, Do, OUT, ld);                 // :257-261,179-180
+  LSTAMP(22);
 }
 
 // GraphPool.forward (AASIST.py:294-322): H (N,D) -> OUT (k,D) in descending score order.
@@ -279,27 +302,40 @@ __device__ void graph_pool(const float* H, int N, int ld, const PoolParams& P, i
   __syncthreads();
 }
 
-// spectral nodes: X[f][c] = max_t |e[c][f][t]| (+ pos[f][c]);  temporal: X[t][c] = max_f |e[c][f][t]|
-__device__ void nodes_max_over_time(const float* e, int C, int NT, const float* pos, float* X,
-                                    int ld) {
+// spectral nodes: XS[f][c] = max_t |e[c][f][t]| (+ pos[f][c]);  temporal: XT[t][c] = max_f |e[c][f][t]|
+// ONE pass over e: a warp owns a channel, lane = time step, the 23 loads of a lane are independent (one L2 latency
+// per channel, not one per row), the column maximum stays in the lane and the 23 row maxima are warp reductions.
+// Either output may be null (RawGAT-ST takes its two node sets from two different encoders).
+__device__ void nodes_from_encoder(const float* e, int C, int NT, const float* pos, float* XS, float* XT, int ld) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int r = warp; r < C * kSpecNodes; r += kWarps) {
-    int c = r / kSpecNodes, f = r % kSpecNodes;
-    const float* row = e + (size_t)r * NT;
-    float m = 0.f;
-    for (int t = lane; t < NT; t += 32) m = fmaxf(m, fabsf(row[t]));
-    m = warp_max(m);
-    if (lane == 0) X[f * ld + c] = m + (pos ? __ldg(pos + f * C + c) : 0.f);
-  }
-  __syncthreads();
-}
-__device__ void nodes_max_over_freq(const float* e, int C, int NT, float* X, int ld) {
-  for (int i = threadIdx.x; i < C * NT; i += kGraphThreads) {
-    int c = i / NT, t = i % NT;
-    const float* col = e + (size_t)c * kSpecNodes * NT + t;
-    float m = 0.f;
-    for (int f = 0; f < kSpecNodes; ++f) m = fmaxf(m, fabsf(col[f * NT]));
-    X[t * ld + c] = m;
+  for (int c = warp; c < C; c += kWarps) {
+    const float* ec = e + (size_t)c * kSpecNodes * NT;
+    float rm[kSpecNodes];
+#pragma unroll
+    for (int f = 0; f < kSpecNodes; ++f) rm[f] = 0.f;
+    for (int t0 = 0; t0 < NT; t0 += 32) {
+      const int t = t0 + lane;
+      const bool ok = t < NT;
+      float v[kSpecNodes];
+#pragma unroll
+      for (int f = 0; f < kSpecNodes; ++f) v[f] = ok ? fabsf(__ldg(ec + f * NT + t)) : 0.f;
+      float cm = 0.f;
+#pragma unroll
+      for (int f = 0; f < kSpecNodes; ++f) {
+        cm = fmaxf(cm, v[f]);
+        rm[f] = fmaxf(rm[f], v[f]);
+      }
+      if (XT && ok) XT[t * ld + c] = cm;
+    }
+    if (XS) {
+      float mine = 0.f;
+#pragma unroll
+      for (int f = 0; f < kSpecNodes; ++f) {
+        const float m = warp_max(rm[f]);
+        if (lane == f) mine = m;
+      }
+      if (lane < kSpecNodes) XS[lane * ld + c] = mine + (pos ? __ldg(pos + lane * C + c) : 0.f);
+    }
   }
   __syncthreads();
 }
@@ -344,9 +380,14 @@ __device__ float* carve_layer_buffers(float*& p, int nmax, int ld, Scratch& S) {
 // ---------------------------------------------------------------------------------------
 // AASIST graph tail (AASIST.py:841-921)
 // ---------------------------------------------------------------------------------------
+// rows of the region [B3 | OT | R]; nmax >= NT, so max(..., nmax) always has room for the parked temporal nodes
+__host__ __device__ inline int aasist_tail_rows(int nmax, int nS, int nT, int nS2, int nT2) {
+  return max((nT2 + nS2) + nT + (nT2 + nS2), nmax);
+}
 __host__ __device__ inline int aasist_graph_smem_floats(int nmax, int ld, int nS, int nT, int nS2,
                                                         int nT2) {
-  int rows = nmax + (nT2 + nS2) + nS + nT + (nT2 + nS2);
+  // B0, OS, then one region [B3 | OT | R] that also holds the temporal nodes (NT rows) until gat_T has consumed them
+  int rows = nmax + nS + aasist_tail_rows(nmax, nS, nT, nS2, nT2);
   return scratch_floats(nmax) + layer_buffer_floats(nmax, ld) + rows * ld + 7 * kMaxDim + 64;
 }
 
@@ -400,19 +441,33 @@ __device__ void speaker_condition_rows(float* R, int n, int ld, int g1, const Sp
   __syncthreads();
 }
 
+#ifdef AASIST_KERNEL_STATS
+#define GSTAMP(k) do { if (threadIdx.x == 0) { long long now_ = clock64(); atomicAdd((unsigned long long*)&g_graph_stats[k], (unsigned long long)(now_ - last_)); last_ = now_; } } while (0)
+#else
+#define GSTAMP(k) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(kGraphThreads)
 aasist_graph_kernel(const GraphArgsAasist a) {
   extern __shared__ __align__(16) float smem[];
+#ifdef AASIST_KERNEL_STATS
+  long long last_ = clock64();
+#endif
   float* p = smem;
   Scratch S;
   carve_scratch(p, a.nmax, a.ld, S);
+#ifdef AASIST_KERNEL_STATS
+  S.tlast = &last_;
+#endif
   const int ld = a.ld;
   float* B0 = bump(p, a.nmax * ld);
   float* B1 = carve_layer_buffers(p, a.nmax, ld, S);
-  float* B3 = bump(p, (a.nT2 + a.nS2) * ld);     // pooled hetero nodes: T rows then S rows
   float* OS = bump(p, a.nS * ld);
-  float* OT = bump(p, a.nT * ld);
-  float* R = bump(p, (a.nT2 + a.nS2) * ld);      // branch-1 result: T rows then S rows
+  float* tail = bump(p, aasist_tail_rows(a.nmax, a.nS, a.nT, a.nS2, a.nT2) * ld);
+  float* B3 = tail;                              // pooled hetero nodes: T rows then S rows
+  float* OT = B3 + (a.nT2 + a.nS2) * ld;
+  float* R = OT + a.nT * ld;                     // branch-1 result: T rows then S rows
+  float* XT = tail;                              // temporal nodes, parked here until gat_T has read them
   float* Rm = bump(p, kMaxDim);
   float* m1 = bump(p, kMaxDim);
   float* m2 = bump(p, kMaxDim);
@@ -439,15 +494,21 @@ aasist_graph_kernel(const GraphArgsAasist a) {
     __syncthreads();
   }
   // spectral graph                                                       (AASIST.py:841-845)
-  nodes_max_over_time(e, a.C, a.NT, a.posS, B0, ld);
+  GSTAMP(0);
+  nodes_from_encoder(e, a.C, a.NT, a.posS, B0, XT, ld);                  // both node sets in one pass over e
+  GSTAMP(1);
   gat_layer(B0, kSpecNodes, ld, a.gatS, B1, S);
+  GSTAMP(2);
   graph_pool(B1, kSpecNodes, ld, a.poolS, a.nS, OS, gi, gw, S);
+  GSTAMP(3);
   if (gi) gi += a.nS;
   if (gw) gw += kSpecNodes;
   // temporal graph                                                       (AASIST.py:848-852)
-  nodes_max_over_freq(e, a.C, a.NT, B0, ld);
-  gat_layer(B0, a.NT, ld, a.gatT, B1, S);
+  GSTAMP(4);
+  gat_layer(XT, a.NT, ld, a.gatT, B1, S);
+  GSTAMP(5);
   graph_pool(B1, a.NT, ld, a.poolT, a.nT, OT, gi, gw, S);
+  GSTAMP(6);
   if (gi) gi += a.nT;
   if (gw) gw += a.NT;
 
@@ -461,14 +522,18 @@ aasist_graph_kernel(const GraphArgsAasist a) {
     for (int d = threadIdx.x; d < a.g0; d += kGraphThreads)
       m0[d] = __ldg((br == 0 ? a.master1 : a.master2) + d);
     __syncthreads();
+    GSTAMP(7);
     htrg_layer(OT, a.nT, OS, a.nS, ld, m0, L1, B0, B1, m1, S);
+    GSTAMP(8);
     graph_pool(B1 + a.nT * ld, a.nS, ld, pS, a.nS2, PS, gi, gw, S);      // pool_hS first (:862)
     if (gi) gi += a.nS2;
     if (gw) gw += a.nS;
     graph_pool(B1, a.nT, ld, pT, a.nT2, PT, gi, gw, S);
     if (gi) gi += a.nT2;
     if (gw) gw += a.nT;
+    GSTAMP(9);
     htrg_layer(PT, a.nT2, PS, a.nS2, ld, m1, L2, B0, B1, m2, S);
+    GSTAMP(10);
     // residual adds (:867-869) and branch-wise max (:890-892)
     const int n2 = a.nT2 + a.nS2;
     for (int t = threadIdx.x; t < n2 * a.g1; t += kGraphThreads) {
@@ -539,6 +604,7 @@ aasist_graph_kernel(const GraphArgsAasist a) {
     if (lane == 0) a.logits[(size_t)b * 2 + o] = logit;
   }
   __syncthreads();   // shared buffers are reused by the next utterance
+  GSTAMP(11);
   }
 }
 
@@ -591,6 +657,24 @@ int launch_graph_aasist(aasist_handle* h, const float* e, int B, int NT, const f
     aasist_graph_kernel<<<balanced_grid(aasist_graph_kernel, B, smem, h->device), kGraphThreads, smem, st>>>(a);
   }
   AASIST_CUDA(cudaGetLastError());
+#ifdef AASIST_KERNEL_STATS
+  if (getenv("AASIST_GRAPH_STATS")) {
+    long long hst[32];
+    AASIST_CUDA(cudaStreamSynchronize(st));
+    AASIST_CUDA(cudaMemcpyFromSymbol(hst, g_graph_stats, sizeof(hst)));
+    static const char* names[12] = {"setup", "nodes_S", "gat_S", "pool_S", "nodes_T", "gat_T", "pool_T", "branch setup",
+                                    "htrg1", "pools_h", "htrg2", "fuse+readout"};
+    fprintf(stderr, "[graph stats] cycles per utterance:");
+    for (int k = 0; k < 12; ++k) fprintf(stderr, " %s %.0f |", names[k], (double)hst[k] / B);
+    static const char* sub[11] = {"(pre)", "gat.att", "gat.softmax", "gat.agg", "gat.linear", "htrg.typeproj", "htrg.att",
+                                  "htrg.softmax", "htrg.master", "htrg.agg", "htrg.linear"};
+    fprintf(stderr, "\n[graph stats] inside the layers:");
+    for (int k = 0; k < 11; ++k) fprintf(stderr, " %s %.0f |", sub[k], (double)hst[12 + k] / B);
+    fprintf(stderr, "\n");
+    long long z[32] = {0};
+    AASIST_CUDA(cudaMemcpyToSymbol(g_graph_stats, z, sizeof(z)));
+  }
+#endif
   return 0;
 }
 
@@ -622,7 +706,7 @@ rawgat_graph_kernel(const GraphArgsRawGat a) {
   const int D1 = a.gatT.Do;  // 32
 
   // "T" branch: max over time -> 23 nodes (:338-341)
-  nodes_max_over_time(eT, 64, a.NT, nullptr, B0, ld);
+  nodes_from_encoder(eT, 64, a.NT, nullptr, B0, nullptr, ld);
   gat_layer(B0, kSpecNodes, ld, a.gatT, B1, S);
   graph_pool(B1, kSpecNodes, ld, a.poolT, a.nT, B0, gi, gw, S);
   if (gi) gi += a.nT;
@@ -636,7 +720,7 @@ rawgat_graph_kernel(const GraphArgsRawGat a) {
   }
   __syncthreads();
   // "S" branch: max over freq -> NT nodes (:343-347)
-  nodes_max_over_freq(eS, 64, a.NT, B0, ld);
+  nodes_from_encoder(eS, 64, a.NT, nullptr, nullptr, B0, ld);
   gat_layer(B0, a.NT, ld, a.gatS, B1, S);
   graph_pool(B1, a.NT, ld, a.poolS, a.nS, B0, gi, gw, S);
   if (gi) gi += a.nS;
