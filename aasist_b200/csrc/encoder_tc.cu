@@ -174,13 +174,18 @@ template <int COP>
 struct ConvCfg {
   static constexpr int kEpiWarps = COP / 4;                 // 8 (COP = 32) or 16 (COP = 64)
   static constexpr int kThreads = 64 + 32 * kEpiWarps;
+  template <int CPI, int MODE>
+  static constexpr bool tma_out() { return MODE == 0 /*TC_CONV1*/ && CPI == 32; }
+  // staging for the TMA-store epilogue: 4 quadrants x 2 buffers x 32 rows x (4*COP) bytes
+  template <int CPI, int MODE>
+  static constexpr int stage_bytes() { return tma_out<CPI, MODE>() ? 4 * 2 * 32 * 4 * COP : 0; }
 };
 
 template <int CPI, int COP, int MODE>
 __global__ void __launch_bounds__(ConvCfg<COP>::kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmS,
                const __grid_constant__ CUtensorMap tmAt, const __grid_constant__ CUtensorMap tmSt,
-               const ConvTcParams p) {
+               const __grid_constant__ CUtensorMap tmO, const ConvTcParams p) {
   constexpr int SLABS = CPI / 32;                    // 128-byte-wide K slabs per input tile
   constexpr int SLOT_BYTES = SLABS * kSlabBytes;
   constexpr int KC = CPI / 16;                       // K chunks (UMMA_K = 16) per product
@@ -193,12 +198,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr int kEpiWarps = ConvCfg<COP>::kEpiWarps;
   constexpr int R_IN = (MODE == TC_CONV1) ? 23 : 24; // input rows walked per strip
   constexpr int NTHREADS = ConvCfg<COP>::kThreads;
+  // CONV1 of a 32-channel input (block 2: the store-heaviest kernel, 14.7 MB per utterance): the epilogue stages
+  // a quadrant's 32 rows in shared memory (SWIZZLE_128B sub-tiles, conflict-free 16-byte stores) and ONE thread
+  // hands them to the TMA (cp.async.bulk.tensor store) -- full 128-byte lines leave the SM without touching the
+  // L1/LSU, which thread-per-row 32-byte st.global kept 87 % busy.  64-channel inputs have no room for the staging.
+  constexpr bool TMA_OUT = ConvCfg<COP>::template tma_out<CPI, MODE>();
+  constexpr int STAGE_SUB = COP / 32;                // 128-byte-wide sub-tiles of a staged row (hi, lo)
+  constexpr int STAGE_BYTES = STAGE_SUB * 32 * 128;  // one quadrant, one buffer
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* s_w = smem;
   uint8_t* s_ring = smem + p.wimg_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + (size_t)p.n_slots * SLOT_BYTES);
+  uint8_t* s_stage = s_ring + (size_t)p.n_slots * SLOT_BYTES;    // 1024-byte aligned: every term is a multiple of 1 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + ConvCfg<COP>::template stage_bytes<CPI, MODE>());
   uint64_t* full = bars;
   uint64_t* empty = bars + kMaxSlots;
   uint64_t* tfull = bars + 2 * kMaxSlots;
@@ -227,6 +240,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     fence_barrier_init();
     prefetch_tensormap(&tmA);
     if (HAS_SIDE) prefetch_tensormap(&tmS);
+    if (TMA_OUT) prefetch_tensormap(&tmO);
     if (p.n_tail) {
       prefetch_tensormap(&tmAt);
       if (HAS_SIDE) prefetch_tensormap(&tmSt);
@@ -447,6 +461,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int col0 = part * 16;
     const float* bias0 = s_bias + col0;
     int tcount = 0;
+    int nstage = 0;                       // TMA-store epilogue: staging steps of this quadrant so far (buffer = nstage & 1)
     for (int t = blockIdx.x; t < n_strips; t += gridDim.x) {
       const bool tail = t >= p.B * p.n_full;
       int jt, b, j;
@@ -503,7 +518,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = 0.f;
               }
-              if (j < p.J) {
+              if (TMA_OUT && !tail) {
+                // stage this thread's 32 B of hi and 32 B of lo in the quadrant's buffer, then one thread issues
+                // the stores of the quadrant's 32 rows (rows >= J are clipped by the tensor map)
+                uint32_t hw[8], lw[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) split_pack2<true>(v[2 * i], v[2 * i + 1], hw[i], lw[i]);
+                uint8_t* sb = s_stage + (size_t)((quad * 2 + (nstage & 1)) * STAGE_BYTES);
+                const uint32_t sw = (uint32_t)(lane & 7);
+                // COP = 64: sub-tile 0 = hi (128 B rows), sub-tile 1 = lo;  COP = 32: one sub-tile, row = [hi | lo]
+                uint8_t* rh = sb + lane * 128;
+                uint8_t* rl = sb + (STAGE_SUB == 2 ? 32 * 128 : 0) + lane * 128;
+                const uint32_t ch = (uint32_t)(col0 / 8), cl = (uint32_t)((STAGE_SUB == 2 ? 0 : COP / 8) + col0 / 8);
+                *reinterpret_cast<uint4*>(rh + ((ch ^ sw) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                *reinterpret_cast<uint4*>(rh + (((ch + 1) ^ sw) << 4)) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+                *reinterpret_cast<uint4*>(rl + ((cl ^ sw) << 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                *reinterpret_cast<uint4*>(rl + (((cl + 1) ^ sw) << 4)) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+                fence_proxy_async_smem();
+                const bool issuer = part == 0 && lane == 0;
+                // the OTHER buffer was handed to the TMA one step ago: its reads must be over before anybody
+                // writes it in the next step, i.e. before this barrier releases
+                if (issuer) tma_store_wait_read<0>();
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * (COP / 16)) : "memory");
+                if (issuer) {
+#pragma unroll
+                  for (int u = 0; u < STAGE_SUB; ++u)
+                    tma_store_5d(&tmO, sb + u * 32 * 128, u * 64, jt * kTileJ + quad * 32, s, h, b);
+                  tma_store_commit();
+                }
+                ++nstage;
+              } else if (j < p.J) {
                 __half* o = p.out + ((((size_t)b * 24 + h) * 3 + s) * p.J + j) * (2 * COP) + col0 + c * 16;
                 store_pair16<true>(o, o + COP, v);
               }
@@ -563,6 +607,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   }
+  if (TMA_OUT) tma_store_wait_read<0>();   // (only the issuing threads have groups pending) smem must outlive the reads
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) {
@@ -844,9 +889,11 @@ static const char* kConvNames[2][6] = {
 
 template <int CPI, int COP, int MODE>
 static int launch_conv(aasist_handle* h, const char* name, const CUtensorMap& tmA, const CUtensorMap& tmS,
-                       const CUtensorMap& tmAt, const CUtensorMap& tmSt, ConvTcParams p, cudaStream_t st) {
+                       const CUtensorMap& tmAt, const CUtensorMap& tmSt, const CUtensorMap& tmO, ConvTcParams p,
+                       cudaStream_t st) {
   constexpr int SLOT = (CPI / 32) * kSlabBytes;
-  const int budget = 227 * 1024 - 1024 /*align*/ - p.wimg_bytes - 512 /*barriers, bias*/;
+  constexpr int STAGE = ConvCfg<COP>::template stage_bytes<CPI, MODE>();
+  const int budget = 227 * 1024 - 1024 /*align*/ - p.wimg_bytes - STAGE - 512 /*barriers, bias*/;
   int n_slots = std::min(kMaxSlots, budget / SLOT);
   if (n_slots < 2) {
     set_error("conv_tc: not enough shared memory for the input ring (weights %d bytes)", p.wimg_bytes);
@@ -858,7 +905,7 @@ static int launch_conv(aasist_handle* h, const char* name, const CUtensorMap& tm
     if (slots_override >= 2 && slots_override <= n_slots) n_slots = slots_override;
   }
   p.n_slots = n_slots;
-  size_t smem = 1024 + (size_t)p.wimg_bytes + (size_t)n_slots * SLOT + 512;
+  size_t smem = 1024 + (size_t)p.wimg_bytes + (size_t)n_slots * SLOT + STAGE + 512;
   auto kern = conv_tc_kernel<CPI, COP, MODE>;
   AASIST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int n_strips = p.B * p.n_full + p.n_tail;
@@ -878,7 +925,7 @@ static int launch_conv(aasist_handle* h, const char* name, const CUtensorMap& tm
   }
   {
     LaunchSpan span(h, name, st);
-    kern<<<grid, ConvCfg<COP>::kThreads, smem, st>>>(tmA, tmS, tmAt, tmSt, p);
+    kern<<<grid, ConvCfg<COP>::kThreads, smem, st>>>(tmA, tmS, tmAt, tmSt, tmO, p);
   }
   AASIST_CUDA(cudaGetLastError());
   if (want_stats) {   // debugging aid: where the MMA warp waits (cycles per output row-tile, mean over CTAs)
@@ -943,7 +990,8 @@ static int run_block_tc(aasist_handle* h, int enc, int index, const __half* in_p
     return sp;
   };
   const StripPlan sp1 = plan_strips(rows1), sp2 = plan_strips(rows2);
-  CUtensorMap tmIn, tmMid, tmInT1, tmMidT, tmInT2;
+  CUtensorMap tmIn, tmMid, tmInT1, tmMidT, tmInT2, tmMidO;
+  memset(&tmMidO, 0, sizeof(tmMidO));
   memset(&tmIn, 0, sizeof(tmIn));
   memset(&tmMid, 0, sizeof(tmMid));
   memset(&tmInT1, 0, sizeof(tmInT1));
@@ -953,6 +1001,7 @@ static int run_block_tc(aasist_handle* h, int enc, int index, const __half* in_p
   if (index > 0 && (rc = make_act_tmap(h, &tmMid, mid, blk.cop, J, 24, nb))) return rc;
   if (index > 0 && (rc = make_act_tmap(h, &tmIn, in_pairs, blk.cpi, J, 23, nb))) return rc;
   if (!fused_path) {
+    if ((rc = make_act_tmap(h, &tmMidO, mid, blk.cop, J, 24, nb, 32))) return rc;   // conv1's TMA stores: 32-row boxes
     if ((rc = make_act_tmap(h, &tmInT1, in_pairs, blk.cpi, J, 23, nb, sp1.seg_rows))) return rc;
     if ((rc = make_act_tmap(h, &tmMidT, mid, blk.cop, J, 24, nb, sp2.seg_rows))) return rc;
     if ((rc = make_act_tmap(h, &tmInT2, in_pairs, blk.cpi, J, 23, nb, sp2.seg_rows))) return rc;
@@ -973,9 +1022,9 @@ static int run_block_tc(aasist_handle* h, int enc, int index, const __half* in_p
     p.n_full = sp1.n_full; p.segs = sp1.segs; p.seg_rows = sp1.seg_rows; p.pieces = sp1.pieces;
     p.piece_cols = sp1.piece_cols; p.n_tail = sp1.n_tail;
     p.bias = blk.c1.bias; p.out = mid; p.wimg = blk.c1.wimg; p.wimg_bytes = blk.c1.wimg_bytes;
-    if (blk.cpi == 32 && blk.cop == 32) rc = launch_conv<32, 32, TC_CONV1>(h, kConvNames[0][index], tmIn, tmIn, tmInT1, tmInT1, p, st);   // 32 -> 24 (AASIST-L)
-    else if (blk.cpi == 32 && blk.cop == 64) rc = launch_conv<32, 64, TC_CONV1>(h, kConvNames[0][index], tmIn, tmIn, tmInT1, tmInT1, p, st);
-    else if (blk.cpi == 64 && blk.cop == 64) rc = launch_conv<64, 64, TC_CONV1>(h, kConvNames[0][index], tmIn, tmIn, tmInT1, tmInT1, p, st);
+    if (blk.cpi == 32 && blk.cop == 32) rc = launch_conv<32, 32, TC_CONV1>(h, kConvNames[0][index], tmIn, tmIn, tmInT1, tmInT1, tmMidO, p, st);   // 32 -> 24 (AASIST-L)
+    else if (blk.cpi == 32 && blk.cop == 64) rc = launch_conv<32, 64, TC_CONV1>(h, kConvNames[0][index], tmIn, tmIn, tmInT1, tmInT1, tmMidO, p, st);
+    else if (blk.cpi == 64 && blk.cop == 64) rc = launch_conv<64, 64, TC_CONV1>(h, kConvNames[0][index], tmIn, tmIn, tmInT1, tmInT1, tmMidO, p, st);
     else { set_error("f16x3 path: unsupported conv1 shape %d->%d", blk.ci, blk.co); rc = AASIST_E_INVALID; }
     if (rc) return rc;
   }
@@ -989,10 +1038,10 @@ static int run_block_tc(aasist_handle* h, int enc, int index, const __half* in_p
   p.bias = blk.c2.bias; p.out = out_pairs; p.out_f32 = out_f32; p.wimg = blk.c2.wimg; p.wimg_bytes = blk.c2.wimg_bytes;
   if (!blk.downsample) {
     p.idn = in_pairs;   // 64 -> 64 identity block (the 32 -> 32 ones took the fused path above)
-    rc = launch_conv<64, 64, TC_CONV2_ID>(h, kConvNames[1][index], tmMid, tmMid, tmMidT, tmMidT, p, st);
+    rc = launch_conv<64, 64, TC_CONV2_ID>(h, kConvNames[1][index], tmMid, tmMid, tmMidT, tmMidT, tmMidO, p, st);
   } else {
-    if (blk.cop == 32) rc = launch_conv<32, 32, TC_CONV2_DS>(h, kConvNames[1][index], tmMid, tmIn, tmMidT, tmInT2, p, st);
-    else rc = launch_conv<64, 64, TC_CONV2_DS>(h, kConvNames[1][index], tmMid, tmIn, tmMidT, tmInT2, p, st);
+    if (blk.cop == 32) rc = launch_conv<32, 32, TC_CONV2_DS>(h, kConvNames[1][index], tmMid, tmIn, tmMidT, tmInT2, tmMidO, p, st);
+    else rc = launch_conv<64, 64, TC_CONV2_DS>(h, kConvNames[1][index], tmMid, tmIn, tmMidT, tmInT2, tmMidO, p, st);
   }
   return rc;
 }
