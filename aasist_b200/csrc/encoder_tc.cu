@@ -129,8 +129,13 @@ struct Pair16 { uint4 h[2], l[2]; };   // 16 channels of an activation: hi and l
 __device__ __forceinline__ Pair16 load_pair16(const __half* hi_src, const __half* lo_src) {
   Pair16 p;
   uint32_t a[8], b[8];
+#ifdef TC_IDN_ALLOC
   ld_global_nc_256(hi_src, a);
   ld_global_nc_256(lo_src, b);
+#else
+  ld_global_na_256(hi_src, a);   // no L1 allocation: the L1 data array is the shared memory the MMAs fetch from
+  ld_global_na_256(lo_src, b);
+#endif
   p.h[0] = make_uint4(a[0], a[1], a[2], a[3]); p.h[1] = make_uint4(a[4], a[5], a[6], a[7]);
   p.l[0] = make_uint4(b[0], b[1], b[2], b[3]); p.l[1] = make_uint4(b[4], b[5], b[6], b[7]);
   return p;
