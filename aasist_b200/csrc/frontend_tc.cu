@@ -16,8 +16,11 @@
 // Both operands use the no-swizzle K-major canonical layout (8-row x 16-byte core matrices):
 //   addr(row, kbyte) = chunk*CHUNK + (row/8)*256 + (kbyte/16)*128 + (row%8)*16 + kbyte%16
 // i.e. SBO = 256 B (next 8-row group), LBO = 128 B (second 16-byte K half of a UMMA_K=16 chunk).
-// The A tile is a 9-slot ring indexed by K chunk: the MMA warp releases chunk kc of tile t
-// (tcgen05.commit) and the producers immediately rebuild it for tile t+1.
+// The A operand lives in TENSOR MEMORY (tcgen05.mma with A in TMEM, ptx.cuh umma_f16_ts): a producer thread owns
+// a tile row = a TMEM lane and writes the 16 (hi,lo) words of a K chunk straight from the staged segment with one
+// tcgen05.st -- the tile is never written to or read from shared memory (it was 73 KB of writes + 108 KB of
+// operand reads per tile next to the 175 KB of filter-operand reads).  The chunks form a 6-slot ring in the 96
+// TMEM columns the two 208-column accumulators leave free; the MMA warp releases a slot with tcgen05.commit.
 #include <stdio.h>
 
 #include <algorithm>
@@ -33,10 +36,11 @@ using namespace ptx;
 constexpr int kFtTile = 128;                  // pooled steps per tile (UMMA M)
 constexpr int kFtN = 208;                     // 23 bands x 9 (3 filters x 3 phases), padded to /16
 constexpr int kFtKC = 9;                      // K chunks of 16: 131 taps+phases -> 144
-constexpr int kFtAChunk = kFtTile * 32;       // bytes of one A K-chunk (hi or lo)
+constexpr int kFtASlots = 6;                  // A-operand ring: K chunks of 16 TMEM columns [hi 8 | lo 8]
 constexpr int kFtBChunk = kFtN * 32;          // bytes of one B K-chunk (hi or lo)
 constexpr int kFtSeg = 3 * kFtTile + 16 * kFtKC;   // staged samples per tile (527 used)
-constexpr int kFtProdWarps = 8;               // 256 producer threads: two per A row (even / odd K chunks)
+static_assert(kFtKC % 3 == 0, "K chunks split over three producer groups");
+constexpr int kFtProdWarps = 12;              // 384 producer threads: three per A row (K chunks kc % 3); the producers bound this kernel
 constexpr int kFtThreads = 64 + 32 * 8 + 32 * kFtProdWarps;
 constexpr int kFtBufCols = 256;               // TMEM column stride between the two accumulators
 constexpr float kFtScale = 1024.f;            // 2^10 on both operands
@@ -52,6 +56,10 @@ struct FrontTcParams {
   long long* stats;        // optional: MMA-warp wait cycles per CTA [total, afull(producers), tempty(epilogue)]
 };
 
+// TMEM column of A-ring slot i: the columns the two accumulators ([0,208) and [256,464)) leave free
+__device__ __forceinline__ uint32_t ft_a_col(int slot) {
+  return (uint32_t)(slot < 3 ? kFtN + 16 * slot : kFtBufCols + kFtN + 16 * (slot - 3));
+}
 // no-swizzle K-major descriptor: LBO = 128 B, SBO = 256 B, version 1, layout 0
 __device__ __forceinline__ uint64_t umma_desc_noswz(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) |
@@ -128,16 +136,13 @@ sinc_frontend_tc_kernel(const FrontTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* s_b = smem;                                         // [2][9][kFtBChunk]
-  uint8_t* s_a = s_b + 2 * kFtKC * kFtBChunk;                  // [9][2][kFtAChunk]  (kc, hi|lo)
-  __half* s_x = reinterpret_cast<__half*>(s_a + 2 * kFtKC * kFtAChunk);   // 4 staged copies of the segment
+  // staged waveform segment, double buffered (tile t+1 is staged while tile t is being built): 4 copies each --
+  // [0] hi, xh0[i] = hi(x[g0+i]); [1] hi shifted by one sample, xh1[i] = xh0[i+1]; [2], [3] the same for lo
+  __half* s_x = reinterpret_cast<__half*>(s_b + 2 * kFtKC * kFtBChunk);
   constexpr int XLEN = kFtSeg + 16;
-  __half* xh0 = s_x;                 // hi, xh0[i] = hi(x[g0+i])
-  __half* xh1 = s_x + XLEN;          // hi shifted by one sample: xh1[i] = xh0[i+1]
-  __half* xl0 = s_x + 2 * XLEN;
-  __half* xl1 = s_x + 3 * XLEN;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_x + 4 * XLEN);
-  uint64_t* afull = bars;            // [9]
-  uint64_t* aempty = bars + kFtKC;   // [9]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_x + 2 * 4 * XLEN);
+  uint64_t* afull = bars;            // [kFtASlots] (kFtKC entries reserved)
+  uint64_t* aempty = bars + kFtKC;   // [kFtASlots]
   uint64_t* tfull = bars + 2 * kFtKC;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
@@ -149,8 +154,8 @@ sinc_frontend_tc_kernel(const FrontTcParams p) {
     reinterpret_cast<uint4*>(s_b)[i] = __ldg(reinterpret_cast<const uint4*>(p.bimg) + i);
   fence_proxy_async_smem();
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kFtKC; ++i) {
-      mbar_init(&afull[i], kFtProdWarps / 2);      // the four warps that own this chunk
+    for (int i = 0; i < kFtASlots; ++i) {
+      mbar_init(&afull[i], 4);                     // the four warps (one per TMEM lane quadrant) that own this chunk
       mbar_init(&aempty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -169,9 +174,10 @@ sinc_frontend_tc_kernel(const FrontTcParams p) {
     // =============================== MMA issuer ==================================
     const bool leader = elect_one();   // the whole schedule runs in this one lane
     if (leader) {
-    const uint32_t a_base = smem_u32(s_a), b_base = smem_u32(s_b);
+    const uint32_t b_base = smem_u32(s_b);
     constexpr uint32_t IDESC = umma_idesc_f16(128, kFtN);
     int tcount = 0;
+    int g = 0;                           // K chunks consumed so far: chunk g lives in ring slot g % kFtASlots
     long long w_te = 0, w_af = 0;
     const long long t_begin = AASIST_CLOCK();
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
@@ -179,24 +185,18 @@ sinc_frontend_tc_kernel(const FrontTcParams p) {
       AASIST_TIMED_WAIT(&tempty[buf], ((tcount >> 1) & 1) ^ 1, w_te);
       tc_fence_after_sync();
       const uint32_t d = tmem_base + (uint32_t)(buf * kFtBufCols);
-      for (int kc = 0; kc < kFtKC; ++kc) {
-        AASIST_TIMED_WAIT(&afull[kc], tcount & 1, w_af);
+      for (int kc = 0; kc < kFtKC; ++kc, ++g) {
+        const int slot = g % kFtASlots;
+        AASIST_TIMED_WAIT(&afull[slot], (g / kFtASlots) & 1, w_af);
         tc_fence_after_sync();
         {
-          const uint64_t a_hi = umma_desc_noswz(a_base + (uint32_t)((2 * kc) * kFtAChunk));
-          const uint64_t a_lo = umma_desc_noswz(a_base + (uint32_t)((2 * kc + 1) * kFtAChunk));
+          const uint32_t a_hi = tmem_base + ft_a_col(slot), a_lo = a_hi + 8;
           const uint64_t b_hi = umma_desc_noswz(b_base + (uint32_t)(kc * kFtBChunk));
           const uint64_t b_lo = umma_desc_noswz(b_base + (uint32_t)((kFtKC + kc) * kFtBChunk));
-          if (p.collector) {
-            umma_f16_keep(d, a_hi, b_hi, IDESC, kc > 0 ? 1u : 0u);
-            umma_f16_reuse(d, a_hi, b_lo, IDESC, 1);                    // same A: taken from the collector
-            umma_f16(d, a_lo, b_hi, IDESC, 1);
-          } else {
-            umma_f16(d, a_hi, b_hi, IDESC, kc > 0 ? 1u : 0u);
-            umma_f16(d, a_lo, b_hi, IDESC, 1);
-            umma_f16(d, a_hi, b_lo, IDESC, 1);
-          }
-          umma_commit(&aempty[kc]);
+          umma_f16_ts(d, a_hi, b_hi, IDESC, kc > 0 ? 1u : 0u);
+          umma_f16_ts(d, a_lo, b_hi, IDESC, 1);
+          umma_f16_ts(d, a_hi, b_lo, IDESC, 1);
+          umma_commit(&aempty[slot]);
         }
       }
       umma_commit(&tfull[buf]);
@@ -222,8 +222,9 @@ sinc_frontend_tc_kernel(const FrontTcParams p) {
     }
   } else if (warp >= 10) {
     // ============ A-operand producers: stage the waveform segment, build the Hankel-like tile ============
-    const int ptid = threadIdx.x - 320;          // 0..255: row = ptid & 127, K-chunk parity = ptid >> 7
-    const int prow = ptid & 127, ppart = ptid >> 7;
+    const int ptid = threadIdx.x - 320;          // 0..255 (staging of the segment)
+    // tile row = TMEM lane: a warp reaches the 32 lanes of quadrant warp % 4; K-chunk parity = warp group
+    const int prow = (warp & 3) * 32 + lane, ppart = (warp - 10) >> 2;
     int tcount = 0;
     constexpr int PER = (kFtSeg + 1 + 32 * kFtProdWarps - 1) / (32 * kFtProdWarps);   // samples per thread (5)
     float pre[PER];
@@ -240,9 +241,12 @@ sinc_frontend_tc_kernel(const FrontTcParams p) {
         pre[q] = (i < kFtSeg + 1 && g < (size_t)p.L) ? __ldg(xb + g) : 0.f;
       }
     };
-    if ((int)blockIdx.x < n_tiles) fetch(blockIdx.x);
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
-      asm volatile("bar.sync 2, %0;" ::"n"(32 * kFtProdWarps) : "memory");   // previous tile fully built
+    // registers -> fp16 pairs in segment buffer `buf`
+    auto stage = [&](int buf) {
+      __half* xh0 = s_x + buf * 4 * XLEN;
+      __half* xh1 = xh0 + XLEN;
+      __half* xl0 = xh0 + 2 * XLEN;
+      __half* xl1 = xh0 + 3 * XLEN;
 #pragma unroll
       for (int q = 0; q < PER; ++q) {
         const int i = ptid + 32 * kFtProdWarps * q;
@@ -258,28 +262,47 @@ sinc_frontend_tc_kernel(const FrontTcParams p) {
           if (i > 0) { xh1[i - 1] = h; xl1[i - 1] = l; }
         }
       }
-      asm volatile("bar.sync 2, %0;" ::"n"(32 * kFtProdWarps) : "memory");
-      if (t + (int)gridDim.x < n_tiles) fetch(t + gridDim.x);
+    };
+    if ((int)blockIdx.x < n_tiles) {
+      fetch(blockIdx.x);
+      stage(0);
+      if ((int)(blockIdx.x + gridDim.x) < n_tiles) fetch(blockIdx.x + gridDim.x);
+    }
+    asm volatile("bar.sync 2, %0;" ::"n"(32 * kFtProdWarps) : "memory");
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
+      // tile t+1 into the other buffer (its last readers, the builders of tile t-1, are behind the barrier that
+      // ended the previous iteration), then the samples of tile t+2 into registers
+      if (t + (int)gridDim.x < n_tiles) {
+        stage((tcount + 1) & 1);
+        if (t + 2 * (int)gridDim.x < n_tiles) fetch(t + 2 * gridDim.x);
+      }
+      const __half* xh0 = s_x + (tcount & 1) * 4 * XLEN;
+      const __half* xh1 = xh0 + XLEN;
+      const __half* xl0 = xh0 + 2 * XLEN;
+      const __half* xl1 = xh0 + 3 * XLEN;
       // row ptid, K halves [8q, 8q+8) = samples 3*ptid + 8q ...; pick the copy that makes the start even
       const int start0 = 3 * prow;
       const bool odd = start0 & 1;
       const uint32_t* srch = reinterpret_cast<const uint32_t*>(odd ? xh1 : xh0) + ((start0 - (odd ? 1 : 0)) >> 1);
       const uint32_t* srcl = reinterpret_cast<const uint32_t*>(odd ? xl1 : xl0) + ((start0 - (odd ? 1 : 0)) >> 1);
-      const uint32_t row_off = (uint32_t)((prow >> 3) * 256 + (prow & 7) * 16);
-      for (int kc = ppart; kc < kFtKC; kc += 2) {
-        mbar_wait(&aempty[kc], (tcount & 1) ^ 1);
-        uint8_t* ah = s_a + (size_t)(2 * kc) * kFtAChunk + row_off;
-        uint8_t* al = ah + kFtAChunk;
+      const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+      for (int kc = ppart; kc < kFtKC; kc += kFtProdWarps / 4) {
+        const int g = tcount * kFtKC + kc, slot = g % kFtASlots;
+        mbar_wait(&aempty[slot], ((g / kFtASlots) & 1) ^ 1);
+        tc_fence_after_sync();
+        uint32_t wv[16];                                 // [hi: K 0..15 | lo: K 0..15] of this row's chunk
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {                 // the two 16-byte K halves of the chunk
-          const int w = (16 * kc + 8 * hf) >> 1;         // word offset of these 8 halves
-          *reinterpret_cast<uint4*>(ah + hf * 128) = make_uint4(srch[w], srch[w + 1], srch[w + 2], srch[w + 3]);
-          *reinterpret_cast<uint4*>(al + hf * 128) = make_uint4(srcl[w], srcl[w + 1], srcl[w + 2], srcl[w + 3]);
+        for (int i = 0; i < 8; ++i) {
+          wv[i] = srch[8 * kc + i];
+          wv[8 + i] = srcl[8 * kc + i];
         }
-        fence_proxy_async_smem();
+        tmem_st16(t_lane + ft_a_col(slot), wv);
+        tmem_st_wait();
+        tc_fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&afull[kc]);
+        if (lane == 0) mbar_arrive(&afull[slot]);
       }
+      asm volatile("bar.sync 2, %0;" ::"n"(32 * kFtProdWarps) : "memory");   // tile t built, tile t+1 staged
     }
   }
   tc_fence_before_sync();
@@ -362,7 +385,7 @@ int launch_frontend_tc(aasist_handle* h, const uint8_t* bimg, int sm_count, cons
   p.x = x; p.out = out; p.bimg = bimg; p.B = B; p.L = L; p.Wp = Wp;
   p.n_tiles_per_utt = (Wp + kFtTile - 1) / kFtTile;
   p.bn_scale = h->bn0_scale; p.bn_shift = h->bn0_shift;
-  const size_t smem = 1024 + 2 * kFtKC * kFtBChunk + 2 * kFtKC * kFtAChunk + 4 * (kFtSeg + 16) * 2 + 256;
+  const size_t smem = 1024 + 2 * kFtKC * kFtBChunk + 2 * 4 * (kFtSeg + 16) * 2 + 256;
   AASIST_CUDA(cudaFuncSetAttribute(sinc_frontend_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = std::min(B * p.n_tiles_per_utt, sm_count);
   static int want_stats = -1;
