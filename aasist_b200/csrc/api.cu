@@ -487,6 +487,7 @@ static void pack_gat(aasist_handle* h, GraphPacker& gp, const std::string& p, in
   g.temp = temp;
   BnFold bn = fold_bn(h, p + ".bn");
   gp.put(&g.attWt, transpose_w(P(h, p + ".att_proj.weight"), D, Do));
+  gp.put(&g.attImg, att_image_floats(P(h, p + ".att_proj.weight"), D, Do));
   gp.put(&g.attB, P(h, p + ".att_proj.bias"));
   gp.put(&g.attW, P(h, p + ".att_weight"));
   gp.put(&g.pWt, transpose_w(P(h, p + ".proj_with_att.weight"), D, Do, &bn.scale));
@@ -508,6 +509,7 @@ static void pack_htrg(aasist_handle* h, GraphPacker& gp, const std::string& p, i
   gp.put(&g.t2Wt, transpose_w(P(h, p + ".proj_type2.weight"), D, D));
   gp.put(&g.t2B, P(h, p + ".proj_type2.bias"));
   gp.put(&g.attWt, transpose_w(P(h, p + ".att_proj.weight"), D, Do));
+  gp.put(&g.attImg, att_image_floats(P(h, p + ".att_proj.weight"), D, Do));
   gp.put(&g.attB, P(h, p + ".att_proj.bias"));
   gp.put(&g.w11, P(h, p + ".att_weight11"));
   gp.put(&g.w22, P(h, p + ".att_weight22"));

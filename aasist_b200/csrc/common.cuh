@@ -100,6 +100,7 @@ struct SpkParams {
 struct GatParams {  // GraphAttentionLayer (AASIST.py:17-110), eval BN folded into the projections
   int D, Do;
   const float* attWt;  // [D][Do]  att_proj.weight^T
+  const float* attImg; // att_proj.weight as an fp16 hi/lo tensor-core operand image (graph.cu att_image_floats)
   const float* attB;   // [Do]
   const float* attW;   // [Do]     att_weight
   const float* pWt;    // [D][Do]  proj_with_att.weight^T    * bn_scale
@@ -112,6 +113,7 @@ struct HtrgParams {  // HtrgGraphAttentionLayer (AASIST.py:113-282)
   int D, Do;
   const float *t1Wt, *t1B, *t2Wt, *t2B;   // proj_type1/2: [D][D], [D]
   const float *attWt, *attB;              // att_proj
+  const float* attImg;                    // att_proj.weight as an fp16 hi/lo tensor-core operand image
   const float *w11, *w22, *w12;           // att_weight11/22/12 [Do]
   const float *attMWt, *attMB, *wM;       // att_projM, att_weightM
   const float *pWt, *qWt, *bias;          // node projection, BN folded
@@ -150,12 +152,14 @@ struct GraphArgsAasist {
   // AASIST-Robust variant (AASIST_Robust.py:248-301): one branch (st11 = ST1, st12 = ST2, poolhS1/poolhT1 =
   // pool_hS/pool_hT), readout without the master node, auxiliary head on mean(e), softmax-weighted ensemble
   int robust;
+  int tc;                  // attention maps on the tensor cores (precision f16x3 / f16x2); 0 = CUDA-core fp32
   const float* auxWt;      // aux_out_layer.weight^T [C][2]
   float auxB0, auxB1, ens0, ens1;
 };
 
 struct GraphArgsRawGat {
   int NT;            // temporal nodes of encoder_S output (29)
+  int tc;            // attention maps on the tensor cores (precision f16x3 / f16x2)
   int ld, nmax;
   const float* eT;   // encoder_T output (B,64,23,NT) -> 23 nodes (max over time)
   const float* eS;   // encoder_S output (B,64,23,NT) -> NT nodes (max over freq)
@@ -273,6 +277,8 @@ int launch_block33_f32(aasist_handle* h, const ConvBlock33F32& blk, const float*
                        float* out, cudaStream_t st);
 int launch_block_f32(aasist_handle* h, const ConvBlockF32& blk, const float* in, int B, int W,
                      float* mid, float* out, cudaStream_t st);
+// att_proj.weight (Do, D) -> fp16 hi/lo operand image for the tensor-core attention maps, as raw bytes in floats
+std::vector<float> att_image_floats(const std::vector<float>& w, int D, int Do);
 int launch_graph_aasist(aasist_handle* h, const float* e, int B, int NT, const float* spk_emb,
                         float* last_hidden, float* logits, int32_t* topk, float* scores, cudaStream_t st);
 int launch_graph_rawgat(aasist_handle* h, const float* eT, const float* eS, int B, int NT,

@@ -8,12 +8,18 @@
 //   a11 RawGAT-ST graph tail            models/RawNetGatSpoofST.py:338-356
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
+
+#include <vector>
 
 #include <algorithm>
 
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace aasist {
+
+using namespace ptx;
 
 constexpr int kGraphThreads = 256;
 constexpr int kWarps = kGraphThreads / 32;
@@ -52,6 +58,13 @@ struct Scratch {
   float* wts;    // [nmax] pool weights (pre-sigmoid) / master logits
   int* idx;      // [nmax]
   float* aggM;   // [kMaxDim]
+  // tensor-core attention maps (att_logits_tc): on/off, TMEM base, completion mbarrier and its phase,
+  // and the partial logits of the second column half of a 128-pair tile
+  int use_tc;
+  uint32_t tmem;
+  uint64_t* mma_bar;
+  uint32_t* mma_phase;
+  float* part;   // [128]
   long long* tlast;   // stats build only: time of the previous stamp (thread 0)
 };
 
@@ -115,6 +128,129 @@ __device__ void att_logits(const float* X, int N, int ld, int D, int Do, const f
     }
   }
   __syncthreads();
+}
+
+// ---- the same attention map on the tensor cores ------------------------------------------------------------
+// pre[p][k] = sum_d (x_i[d] x_j[d]) W[k][d] is a GEMM: M = node pairs (tiles of 128), K = D, N = Do.  A thread owns
+// a pair = a TMEM lane: it forms the D products in fp32, splits them into fp16 (hi, lo) and writes them straight
+// into tensor memory as the A operand (tcgen05.st); B = att_proj.weight as an fp16 (hi, lo) image staged in shared
+// memory (where the fp32 path keeps its transposed copy); three products per K chunk (hi*hi + lo*hi + hi*lo, fp32
+// accumulation -- the scheme of the encoder, ~2^-22 relative); the accumulator row comes back to the same thread
+// for bias, tanh, the dot product with the attention weight and the symmetric store.  Warps w and w+4 share a lane
+// quadrant: each builds half of the K chunks and reduces half of the output columns.
+constexpr int kAttTmemCols = 128;      // [0,64) A operand: 16 columns per K chunk [hi 8 | lo 8];  [64,128) accumulator
+__host__ __device__ inline int att_pad16(int v) { return (v + 15) & ~15; }
+__device__ __forceinline__ uint64_t att_desc_noswz(uint32_t smem_addr) {   // K-major, no swizzle: LBO 128 B, SBO 256 B
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) |
+         ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void tmem_ld8_async(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait8(uint32_t (&r)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+               :
+               : "memory");
+}
+
+__device__ void att_logits_tc(const float* X, int N, int ld, int D, int Do, const float* attImg,
+                              const float* attB, const float* w11, const float* w22, const float* w12, int n1,
+                              float temp, const Scratch& S) {
+  const int Dp = att_pad16(D), Dop = att_pad16(Do), KC = Dp >> 4;
+  const int chunk_bytes = Dop * 32;
+  // operand image [hi: KC chunks][lo: KC chunks] of [Dop rows x 32 B] -> shared memory (aliases the layer buffers)
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(attImg);
+    uint4* dst = reinterpret_cast<uint4*>(S.Wst);
+    for (int i = threadIdx.x; i < 2 * KC * chunk_bytes / 16; i += kGraphThreads) dst[i] = __ldg(src + i);
+  }
+  for (int k = threadIdx.x; k < Dop; k += kGraphThreads) {
+    const bool ok = k < Do;
+    S.vb[k] = ok ? attB[k] : 0.f;
+    S.va[k] = ok ? w11[k] : 0.f;
+    S.vb2[k] = ok ? w22[k] : 0.f;
+    S.vc[k] = ok ? w12[k] : 0.f;
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int quad = warp & 3, half = warp >> 2;
+  const int pairs = N * (N + 1) / 2;
+  const uint32_t t_lane = S.tmem + ((uint32_t)(quad * 32) << 16);
+  const uint32_t img = smem_u32(S.Wst);
+  // K chunks of this half: [kc0, kc1)
+  const int kc0 = half == 0 ? 0 : (KC + 1) / 2, kc1 = half == 0 ? (KC + 1) / 2 : KC;
+  const int nc = Dop >> 1;                     // accumulator columns of this half: 8, 16, 24 or 32
+  for (int base = 0; base < pairs; base += 128) {
+    int p = base + quad * 32 + lane;
+    const bool valid = p < pairs;
+    if (!valid) p = 0;
+    // decode p -> (i, j), i <= j, row-major upper triangle; start(i) = i*(2N-i+1)/2
+    const float fn = (float)(2 * N + 1);
+    int i = (int)((fn - sqrtf(fn * fn - 8.f * (float)p)) * 0.5f);
+    i = max(0, min(i, N - 1));
+    while (i + 1 < N && (i + 1) * (2 * N - i) / 2 <= p) ++i;
+    while (i > 0 && i * (2 * N - i + 1) / 2 > p) --i;
+    const int j = i + (p - i * (2 * N - i + 1) / 2);
+    const float* xi = X + i * ld;
+    const float* xj = X + j * ld;
+    for (int kc = kc0; kc < kc1; ++kc) {
+      uint32_t w[16];                          // [hi: K 0..15 | lo: K 0..15] of this pair's chunk
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int d = 16 * kc + 2 * q;
+        const float a0 = d < D ? xi[d] * xj[d] : 0.f;
+        const float a1 = d + 1 < D ? xi[d + 1] * xj[d + 1] : 0.f;
+        split2_sat(a0, a1, w[q], w[8 + q]);
+      }
+      tmem_st16(t_lane + (uint32_t)(16 * kc), w);
+    }
+    tmem_st_wait();
+    tc_fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tc_fence_after_sync();
+      const uint32_t idesc = umma_idesc_f16(128, Dop);
+      for (int kc = 0; kc < KC; ++kc) {
+        const uint64_t b_hi = att_desc_noswz(img + (uint32_t)(kc * chunk_bytes));
+        const uint64_t b_lo = att_desc_noswz(img + (uint32_t)((KC + kc) * chunk_bytes));
+        const uint32_t a_hi = S.tmem + (uint32_t)(16 * kc), a_lo = a_hi + 8;
+        umma_f16_ts(S.tmem + 64u, a_hi, b_hi, idesc, kc > 0 ? 1u : 0u);
+        umma_f16_ts(S.tmem + 64u, a_lo, b_hi, idesc, 1);
+        umma_f16_ts(S.tmem + 64u, a_hi, b_lo, idesc, 1);
+      }
+      umma_commit(S.mma_bar);
+    }
+    mbar_wait(S.mma_bar, *S.mma_phase);
+    tc_fence_after_sync();
+    // this half's accumulator columns [half*nc, half*nc + nc): bias, tanh, dot with the attention weight
+    const float* wsel = (j < n1) ? S.va : ((i >= n1) ? S.vb2 : S.vc);
+    float logit = 0.f;
+    for (int c = 0; c < nc; c += 8) {
+      uint32_t acc[8];
+      tmem_ld8_async(t_lane + 64u + (uint32_t)(half * nc + c), acc);
+      tmem_ld_wait8(acc);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int k = half * nc + c + q;
+        logit = fmaf(wsel[k], tanhf(__uint_as_float(acc[q]) + S.vb[k]), logit);
+      }
+    }
+    if (half == 1) S.part[quad * 32 + lane] = logit;
+    tc_fence_before_sync();
+    __syncthreads();                           // partial sums visible; accumulator and A columns free for the next tile
+    if (threadIdx.x == 0) *S.mma_phase ^= 1u;
+    if (half == 0 && valid) {
+      logit = (logit + S.part[quad * 32 + lane]) / temp;
+      S.A[i * S.lda + j] = logit;
+      S.A[j * S.lda + i] = logit;
+    }
+    __syncthreads();                           // phase flip and S.part reads ordered before the next tile
+  }
 }
 
 // softmax over j of every row i (F.softmax(att_map, dim=-2), AASIST.py:89)
@@ -188,7 +324,8 @@ __device__ void linear_rows(const float* IN, const float* IN2, int n, int ldin, 
 __device__ void gat_layer(const float* X, int N, int ld, const GatParams& P, float* OUT,
                           const Scratch& S) {
   LSTAMP(12);
-  att_logits(X, N, ld, P.D, P.Do, P.attWt, P.attB, P.attW, P.attW, P.attW, N, P.temp, S);
+  if (S.use_tc) att_logits_tc(X, N, ld, P.D, P.Do, P.attImg, P.attB, P.attW, P.attW, P.attW, N, P.temp, S);
+  else att_logits(X, N, ld, P.D, P.Do, P.attWt, P.attB, P.attW, P.attW, P.attW, N, P.temp, S);
   LSTAMP(13);
   softmax_rows(N, S);
   LSTAMP(14);
@@ -209,7 +346,8 @@ __device__ void htrg_layer(const float* X1, int n1, const float* X2, int n2, int
   linear_rows<false>(X1, nullptr, n1, ld, D, P.t1Wt, nullptr, P.t1B, D, HX, ld);              // :158
   linear_rows<false>(X2, nullptr, n2, ld, D, P.t2Wt, nullptr, P.t2B, D, HX + n1 * ld, ld);    // :159
   LSTAMP(17);
-  att_logits(HX, N, ld, D, Do, P.attWt, P.attB, P.w11, P.w22, P.w12, n1, P.temp, S);          // :225-251
+  if (S.use_tc) att_logits_tc(HX, N, ld, D, Do, P.attImg, P.attB, P.w11, P.w22, P.w12, n1, P.temp, S);
+  else att_logits(HX, N, ld, D, Do, P.attWt, P.attB, P.w11, P.w22, P.w12, n1, P.temp, S);     // :225-251
   LSTAMP(18);
   softmax_rows(N, S);                                                                        // :253
   LSTAMP(19);
@@ -348,7 +486,7 @@ __device__ __forceinline__ float* bump(float*& p, int n) {
 
 __host__ __device__ inline int scratch_floats(int nmax) {
   int lda = nmax + 1;
-  return 4 * kMaxDim + ((nmax * lda + 3) & ~3) + 3 * ((nmax + 3) & ~3) + kMaxDim;
+  return 4 * kMaxDim + ((nmax * lda + 3) & ~3) + 3 * ((nmax + 3) & ~3) + kMaxDim + 128 + 8;
 }
 
 __device__ void carve_scratch(float*& p, int nmax, int ld, Scratch& S) {
@@ -363,6 +501,12 @@ __device__ void carve_scratch(float*& p, int nmax, int ld, Scratch& S) {
   S.wts = bump(p, nmax);
   S.idx = reinterpret_cast<int*>(bump(p, nmax));
   S.aggM = bump(p, kMaxDim);
+  S.part = bump(p, 128);
+  float* ctl = bump(p, 8);                   // mbarrier (8 bytes, 8-byte aligned: every bump is a multiple of 16 B), phase, TMEM base
+  S.mma_bar = reinterpret_cast<uint64_t*>(ctl);
+  S.mma_phase = reinterpret_cast<uint32_t*>(ctl + 2);
+  S.tmem = 0;
+  S.use_tc = 0;
   S.AGG = nullptr;
 }
 
@@ -375,6 +519,30 @@ __device__ float* carve_layer_buffers(float*& p, int nmax, int ld, Scratch& S) {
   S.Wst = region;
   S.AGG = region + nmax * ld;
   return region;                          // B1
+}
+
+// tensor memory + completion barrier for att_logits_tc (all threads; one allocation per CTA for its lifetime)
+__device__ void att_tc_begin(Scratch& S) {
+  uint32_t* slot = S.mma_phase + 1;
+  if (threadIdx.x == 0) {
+    mbar_init(S.mma_bar, 1);
+    *S.mma_phase = 0;
+    fence_barrier_init();
+  }
+  if (threadIdx.x < 32) tmem_alloc<kAttTmemCols>(slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  S.tmem = *slot;
+  S.use_tc = 1;
+}
+__device__ void att_tc_end(const Scratch& S) {
+  tc_fence_before_sync();
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    tc_fence_after_sync();
+    tmem_dealloc<kAttTmemCols>(S.tmem);
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -459,6 +627,7 @@ aasist_graph_kernel(const GraphArgsAasist a) {
 #ifdef AASIST_KERNEL_STATS
   S.tlast = &last_;
 #endif
+  if (a.tc) att_tc_begin(S);
   const int ld = a.ld;
   float* B0 = bump(p, a.nmax * ld);
   float* B1 = carve_layer_buffers(p, a.nmax, ld, S);
@@ -606,6 +775,29 @@ aasist_graph_kernel(const GraphArgsAasist a) {
   __syncthreads();   // shared buffers are reused by the next utterance
   GSTAMP(11);
   }
+  if (a.tc) att_tc_end(S);
+}
+
+// att_proj.weight (Do, D) -> the B operand of att_logits_tc: [hi: KC chunks][lo: KC chunks] of [Dop rows x 32 B] in
+// the no-swizzle K-major canonical layout (8-row x 16-byte core matrices), D and Do padded to multiples of 16
+std::vector<float> att_image_floats(const std::vector<float>& w, int D, int Do) {
+  const int Dp = att_pad16(D), Dop = att_pad16(Do), KC = Dp / 16;
+  const size_t chunk = (size_t)Dop * 32;
+  std::vector<uint8_t> img(2 * KC * chunk, 0);
+  for (int n = 0; n < Do; ++n)
+    for (int k = 0; k < D; ++k) {
+      const float v = w[(size_t)n * D + k];
+      const __half hi = __float2half_rn(v);
+      const __half lo = __float2half_rn(v - __half2float(hi));
+      const int kc = k / 16, kb = (k % 16) * 2;
+      const size_t off = (size_t)kc * chunk + (size_t)(n / 8) * 256 + (size_t)(kb / 16) * 128 + (size_t)(n % 8) * 16 +
+                         (size_t)(kb % 16);
+      memcpy(&img[off], &hi, 2);
+      memcpy(&img[(size_t)KC * chunk + off], &lo, 2);
+    }
+  std::vector<float> out(img.size() / 4);
+  memcpy(out.data(), img.data(), img.size());
+  return out;
 }
 
 // grid for a per-utterance kernel: as many CTAs as utterances up to the resident capacity, then the smallest
@@ -615,6 +807,19 @@ template <typename Kernel>
 static int balanced_grid(Kernel kern, int B, size_t smem, int device) {
   int per_sm = 1, sms = 148;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kGraphThreads, smem);
+  {
+    // a kernel that contains tcgen05.alloc is reported as ONE block per SM by the occupancy API, whatever it
+    // allocates; the hardware co-schedules blocks as long as their allocations fit the 512 columns (a block whose
+    // allocation does not fit waits in tcgen05.alloc).  Resident blocks: shared memory (+1 KB reserved per block),
+    // registers (64 per thread), tensor memory (kAttTmemCols per block)
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, kern) == cudaSuccess) {
+      const int by_smem = (int)((size_t)227 * 1024 / (smem + 1024));
+      const int by_regs = 65536 / (std::max(fa.numRegs, 1) * kGraphThreads);
+      const int by_tmem = 512 / kAttTmemCols;
+      per_sm = std::max(per_sm, std::max(1, std::min(std::min(by_smem, by_regs), std::min(by_tmem, 2048 / kGraphThreads))));
+    }
+  }
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   const int slots = std::max(1, per_sm * sms);
   const int waves = (B + slots - 1) / slots;
@@ -626,6 +831,7 @@ int launch_graph_aasist(aasist_handle* h, const float* e, int B, int NT, const f
   GraphArgsAasist a = h->ga;
   const aasist_config& c = h->cfg;
   a.NT = NT;
+  a.tc = h->cfg.precision != AASIST_PREC_FP32;   // tensor-core attention maps with the split-fp16 precisions
   a.spk_emb = spk_emb;
   a.nS = pooled_count(kSpecNodes, c.pool_ratios[0], 1);
   a.nT = pooled_count(NT, c.pool_ratios[1], 1);
@@ -691,6 +897,7 @@ rawgat_graph_kernel(const GraphArgsRawGat a) {
   float* p = smem;
   Scratch S;
   carve_scratch(p, a.nmax, a.ld, S);
+  if (a.tc) att_tc_begin(S);
   const int ld = a.ld;
   float* B0 = bump(p, a.nmax * ld);
   float* B1 = carve_layer_buffers(p, a.nmax, ld, S);
@@ -754,6 +961,7 @@ rawgat_graph_kernel(const GraphArgsRawGat a) {
     for (int n = 0; n < a.nST; ++n) s = fmaf(__ldg(a.outW + threadIdx.x * a.nST + n), pr[n], s);
     a.logits[(size_t)b * 2 + threadIdx.x] = s + __ldg(a.outB + threadIdx.x);
   }
+  if (a.tc) att_tc_end(S);
 }
 
 int launch_graph_rawgat(aasist_handle* h, const float* eT, const float* eS, int B, int NT,
@@ -761,6 +969,7 @@ int launch_graph_rawgat(aasist_handle* h, const float* eT, const float* eS, int 
                         cudaStream_t st) {
   GraphArgsRawGat a = h->gr;
   a.NT = NT;
+  a.tc = h->cfg.precision != AASIST_PREC_FP32;
   a.nT = pooled_count(kSpecNodes, 0.64, 2);
   a.nS = pooled_count(NT, 0.81, 2);
   a.nST = pooled_count(12, 0.64, 2);
