@@ -615,7 +615,7 @@ __device__ void speaker_condition_rows(float* R, int n, int ld, int g1, const Sp
 #define GSTAMP(k) do { } while (0)
 #endif
 
-__global__ void __launch_bounds__(kGraphThreads)
+__global__ void __launch_bounds__(kGraphThreads, 4)
 aasist_graph_kernel(const GraphArgsAasist a) {
   extern __shared__ __align__(16) float smem[];
 #ifdef AASIST_KERNEL_STATS
@@ -891,7 +891,7 @@ __host__ __device__ inline int rawgat_graph_smem_floats(int nmax, int ld) {
   return scratch_floats(nmax) + layer_buffer_floats(nmax, ld) + (nmax + 2 * 12 + 12 + 12) * ld + 64;
 }
 
-__global__ void __launch_bounds__(kGraphThreads)
+__global__ void __launch_bounds__(kGraphThreads, 4)
 rawgat_graph_kernel(const GraphArgsRawGat a) {
   extern __shared__ __align__(16) float smem[];
   float* p = smem;
