@@ -55,7 +55,8 @@ enum {
   AASIST_ENC_RESIDUAL33 = 2  /* the fork's 3x3 Residual_block, models/AASIST.py:672-725 (AASIST-Robust) */
 };
 
-/* arithmetic of the sinc / encoder convolutions (graph stages are always fp32) */
+/* arithmetic of the sinc / encoder convolutions and of the graph stages' attention projections (everything else
+ * in the graph stages is always fp32) */
 enum {
   AASIST_PREC_FP32 = 0,   /* fp32 FFMA on CUDA cores                                         */
   AASIST_PREC_F16X3 = 1,  /* tcgen05 tensor cores: fp16 hi/lo operand split, 3 products,
