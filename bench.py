@@ -344,8 +344,8 @@ def run_native(args):
     x = 0.05 * torch.randn(B, L_SAMPLES, device=dev, generator=g)
     K = args.steps
     W = max(3, args.warmup)
-    local = torch.empty(K * B, device=dev)                       # this rank's scores of the timed region
-    gathered = torch.empty(world * K * B, device=dev) if world > 1 else None
+    local = torch.empty(max(K, W) * B, device=dev)               # this rank's scores of the timed region (the warm-up reuses it)
+    gathered = torch.empty(world * max(K, W) * B, device=dev) if world > 1 else None
 
     def run_steps(k):
         for i in range(k):
@@ -386,10 +386,11 @@ def run_native(args):
         e2e = None
         if not args.no_e2e:
             xh = x.cpu().pin_memory()
-            host_scores = torch.empty(world * K * B).pin_memory()
+            KE = max(K, 2)                                        # the e2e warm-up submits two batches
+            host_scores = torch.empty(world * KE * B).pin_memory()
 
             def run_e2e(k):
-                model.score_begin(K * B, B, L_SAMPLES, dev)      # same capacity in the warm-up: no allocation when timed
+                model.score_begin(KE * B, B, L_SAMPLES, dev)     # same capacity in the warm-up: no allocation when timed
                 for _ in range(k):
                     model.score_submit(xh)
                 out = model.score_finish(on_device=True)
