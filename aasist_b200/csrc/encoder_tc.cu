@@ -87,6 +87,10 @@ struct TcState {
   int sm_count = 148;
   void* encode_fn = nullptr;  // cuTensorMapEncodeTiled
   uint8_t* front_bimg = nullptr;  // sinc filter operand image (frontend_tc.cu)
+  // second stream of an encoder pass (tc_encode): the two halves of a pass run on two streams so that the
+  // partial last wave of one half's kernel is filled by the other half's kernels
+  cudaStream_t st2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {   // one MUFU.EX2, flush-to-zero, no range branches
@@ -854,6 +858,7 @@ void tc_destroy(aasist_handle* h) {
       cudaFree(b.b0_img);
     }
   cudaFree(h->tc->front_bimg);
+  if (h->tc->st2) { cudaStreamDestroy(h->tc->st2); cudaEventDestroy(h->tc->ev_fork); cudaEventDestroy(h->tc->ev_join); }
   delete h->tc;
   h->tc = nullptr;
 }
@@ -1072,21 +1077,54 @@ int tc_encode(aasist_handle* h, const float* x, int B, int L, float** enc_out, v
   act[1] = (__half*)w;
   const int C = h->cfg.enc_channels[5][1];
   const size_t enc_per = (size_t)C * kSpecNodes * pl.W[6];
-  for (int b0 = 0; b0 < B; b0 += nbmax) {
-    const int nb = std::min(nbmax, B - b0);
-    static int f32_front = -1;   // AASIST_TC_F32_FRONT=1: timing experiments with the CUDA-core sinc stage
-    if (f32_front < 0) { const char* e = getenv("AASIST_TC_F32_FRONT"); f32_front = e ? atoi(e) : 0; }
-    int rc = f32_front ? launch_frontend_f32(h, x + (size_t)b0 * L, nb, L, z, mask_start, mask_count, st)
-                       : launch_frontend_tc(h, bimg, h->tc->sm_count, x + (size_t)b0 * L, nb, L, z, st);
+  static int f32_front = -1;   // AASIST_TC_F32_FRONT=1: timing experiments with the CUDA-core sinc stage
+  if (f32_front < 0) { const char* e = getenv("AASIST_TC_F32_FRONT"); f32_front = e ? atoi(e) : 0; }
+  // The two halves of a pass run on two streams: every kernel here is persistent with one CTA per SM, so the
+  // partial last wave of one half's kernel (blocks 3-5: 86-92 % wave efficiency at 512 x 4 s) is filled by the other
+  // half's kernels instead of idling (+1.6 % on the step).  AASIST_TC_STREAMS=1 runs the pass on one stream.
+  static int two_streams = -1;
+  if (two_streams < 0) { const char* e = getenv("AASIST_TC_STREAMS"); two_streams = e ? (atoi(e) != 1) : 1; }
+  // utterances [u0, u0+n) of the pass that starts at b0, in the slice of every scratch buffer that starts at
+  // utterance u0 of the pass
+  auto run_range = [&](int b0, int u0, int n, cudaStream_t s) -> int {
+    float* zz = (float*)((char*)z + pl.z * u0);
+    __half* mm = (__half*)((char*)mid + pl.mid * u0);
+    __half* aa[2] = {(__half*)((char*)act[0] + pl.act * u0), (__half*)((char*)act[1] + pl.act * u0)};
+    const float* xx = x + (size_t)(b0 + u0) * L;
+    int rc = f32_front ? launch_frontend_f32(h, xx, n, L, zz, mask_start, mask_count, s)
+                       : launch_frontend_tc(h, bimg, h->tc->sm_count, xx, n, L, zz, s);
     if (rc) return rc;
     for (int e = 0; e < h->n_encoders; ++e) {
       const __half* in = nullptr;
       for (int i = 0; i < 6; ++i) {
-        __half* out = act[i & 1];
-        float* of32 = i == 5 ? enc_out[e] + (size_t)b0 * enc_per : nullptr;
-        if ((rc = run_block_tc(h, e, i, in, z, nb, pl.W[i], mid, out, of32, st))) return rc;
+        __half* out = aa[i & 1];
+        float* of32 = i == 5 ? enc_out[e] + (size_t)(b0 + u0) * enc_per : nullptr;
+        if ((rc = run_block_tc(h, e, i, in, zz, n, pl.W[i], mm, out, of32, s))) return rc;
         in = out;
       }
+    }
+    return 0;
+  };
+  for (int b0 = 0; b0 < B; b0 += nbmax) {
+    const int nb = std::min(nbmax, B - b0);
+    int rc;
+    // per-kernel profiling wants kernels that do not overlap; tiny passes gain nothing
+    if (two_streams && !h->profiling && nb >= 64 && (pl.mid % 16 == 0) && (pl.act % 16 == 0)) {   // (TMA bases: 16-byte aligned)
+      TcState* tc = h->tc;
+      if (!tc->st2) {
+        AASIST_CUDA(cudaStreamCreateWithFlags(&tc->st2, cudaStreamNonBlocking));
+        AASIST_CUDA(cudaEventCreateWithFlags(&tc->ev_fork, cudaEventDisableTiming));
+        AASIST_CUDA(cudaEventCreateWithFlags(&tc->ev_join, cudaEventDisableTiming));
+      }
+      const int na = nb / 2;
+      AASIST_CUDA(cudaEventRecord(tc->ev_fork, st));
+      AASIST_CUDA(cudaStreamWaitEvent(tc->st2, tc->ev_fork, 0));
+      if ((rc = run_range(b0, 0, na, st))) return rc;
+      if ((rc = run_range(b0, na, nb - na, tc->st2))) return rc;
+      AASIST_CUDA(cudaEventRecord(tc->ev_join, tc->st2));
+      AASIST_CUDA(cudaStreamWaitEvent(st, tc->ev_join, 0));
+    } else if ((rc = run_range(b0, 0, nb, st))) {
+      return rc;
     }
   }
   return 0;
