@@ -50,6 +50,14 @@ if "--traffic-json" in sys.argv:
     dst, model, batch = a[a.index("--traffic-json") + 1], a[a.index("--model") + 1], int(a[a.index("--batch") + 1])
     names = a[a.index("--names") + 1].split(",")
     assert len(names) == len(out), (len(names), len(out))
+    # "name:utterances" overrides --batch for one launch; launches with the same name (the two half-pass launches of
+    # a kernel) are summed first
+    merged = {}
+    for n, d in zip(names, out):
+        nm, _, nb = n.partition(":")
+        m = merged.setdefault(nm, {"bytes": 0.0, "utts": 0})
+        m["bytes"] += d["dram_rd"] + d["dram_wr"]
+        m["utts"] += int(nb) if nb else batch
     try:
         tr = json.load(open(dst))
     except Exception:
@@ -60,8 +68,9 @@ if "--traffic-json" in sys.argv:
     if tr.get("source_digest16") != sha:
         tr = {"bytes_per_utterance": {}}
     tr["source_digest16"] = sha
-    tr["source"] = f"ncu --set full, one {batch}-utterance launch per kernel ({os.path.basename(path)}); bytes = dram__bytes_read.sum + dram__bytes_write.sum"
-    tr["bytes_per_utterance"][model] = {n: int((d["dram_rd"] + d["dram_wr"]) / batch) for n, d in zip(names, out)}
-    tr["bytes_per_utterance"][model]["_total"] = int(sum(d["dram_rd"] + d["dram_wr"] for d in out) / batch)
+    tr["source"] = (f"ncu --set full, {len(out)} launches of one forward over {batch} utterances ({os.path.basename(path)}), launches of the "
+                    "same kernel summed; bytes = dram__bytes_read.sum + dram__bytes_write.sum")
+    tr["bytes_per_utterance"][model] = {n: int(m["bytes"] / m["utts"]) for n, m in merged.items()}
+    tr["bytes_per_utterance"][model]["_total"] = sum(tr["bytes_per_utterance"][model].values())
     json.dump(tr, open(dst, "w"), indent=1)
     print("wrote", dst)
