@@ -89,8 +89,8 @@ struct TcState {
   uint8_t* front_bimg = nullptr;  // sinc filter operand image (frontend_tc.cu)
   // second stream of an encoder pass (tc_encode): the two halves of a pass run on two streams so that the
   // partial last wave of one half's kernel is filled by the other half's kernels
-  cudaStream_t st2 = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t st2[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {   // one MUFU.EX2, flush-to-zero, no range branches
@@ -858,7 +858,9 @@ void tc_destroy(aasist_handle* h) {
       cudaFree(b.b0_img);
     }
   cudaFree(h->tc->front_bimg);
-  if (h->tc->st2) { cudaStreamDestroy(h->tc->st2); cudaEventDestroy(h->tc->ev_fork); cudaEventDestroy(h->tc->ev_join); }
+  for (int k = 0; k < 3; ++k)
+    if (h->tc->st2[k]) { cudaStreamDestroy(h->tc->st2[k]); cudaEventDestroy(h->tc->ev_join[k]); }
+  if (h->tc->ev_fork) cudaEventDestroy(h->tc->ev_fork);
   delete h->tc;
   h->tc = nullptr;
 }
@@ -1081,9 +1083,10 @@ int tc_encode(aasist_handle* h, const float* x, int B, int L, float** enc_out, v
   if (f32_front < 0) { const char* e = getenv("AASIST_TC_F32_FRONT"); f32_front = e ? atoi(e) : 0; }
   // The two halves of a pass run on two streams: every kernel here is persistent with one CTA per SM, so the
   // partial last wave of one half's kernel (blocks 3-5: 86-92 % wave efficiency at 512 x 4 s) is filled by the other
-  // half's kernels instead of idling (+1.6 % on the step).  AASIST_TC_STREAMS=1 runs the pass on one stream.
-  static int two_streams = -1;
-  if (two_streams < 0) { const char* e = getenv("AASIST_TC_STREAMS"); two_streams = e ? (atoi(e) != 1) : 1; }
+  // half's kernels instead of idling (+1.6 % on the step).  AASIST_TC_STREAMS=1 runs the pass on one stream, 3 / 4
+  // split it further.
+  static int n_streams = -1;
+  if (n_streams < 0) { const char* e = getenv("AASIST_TC_STREAMS"); n_streams = e ? std::min(4, std::max(1, atoi(e))) : 2; }
   // utterances [u0, u0+n) of the pass that starts at b0, in the slice of every scratch buffer that starts at
   // utterance u0 of the pass
   auto run_range = [&](int b0, int u0, int n, cudaStream_t s) -> int {
@@ -1109,20 +1112,25 @@ int tc_encode(aasist_handle* h, const float* x, int B, int L, float** enc_out, v
     const int nb = std::min(nbmax, B - b0);
     int rc;
     // per-kernel profiling wants kernels that do not overlap; tiny passes gain nothing
-    if (two_streams && !h->profiling && nb >= 64 && (pl.mid % 16 == 0) && (pl.act % 16 == 0)) {   // (TMA bases: 16-byte aligned)
+    if (n_streams > 1 && !h->profiling && nb >= 32 * n_streams && (pl.mid % 16 == 0) && (pl.act % 16 == 0)) {   // (TMA bases: 16-byte aligned)
       TcState* tc = h->tc;
-      if (!tc->st2) {
-        AASIST_CUDA(cudaStreamCreateWithFlags(&tc->st2, cudaStreamNonBlocking));
-        AASIST_CUDA(cudaEventCreateWithFlags(&tc->ev_fork, cudaEventDisableTiming));
-        AASIST_CUDA(cudaEventCreateWithFlags(&tc->ev_join, cudaEventDisableTiming));
-      }
-      const int na = nb / 2;
+      if (!tc->ev_fork) AASIST_CUDA(cudaEventCreateWithFlags(&tc->ev_fork, cudaEventDisableTiming));
+      for (int k = 0; k < n_streams - 1; ++k)
+        if (!tc->st2[k]) {
+          AASIST_CUDA(cudaStreamCreateWithFlags(&tc->st2[k], cudaStreamNonBlocking));
+          AASIST_CUDA(cudaEventCreateWithFlags(&tc->ev_join[k], cudaEventDisableTiming));
+        }
       AASIST_CUDA(cudaEventRecord(tc->ev_fork, st));
-      AASIST_CUDA(cudaStreamWaitEvent(tc->st2, tc->ev_fork, 0));
-      if ((rc = run_range(b0, 0, na, st))) return rc;
-      if ((rc = run_range(b0, na, nb - na, tc->st2))) return rc;
-      AASIST_CUDA(cudaEventRecord(tc->ev_join, tc->st2));
-      AASIST_CUDA(cudaStreamWaitEvent(st, tc->ev_join, 0));
+      int u0 = 0;
+      for (int k = 0; k < n_streams; ++k) {
+        const int n = (nb - u0) / (n_streams - k);
+        cudaStream_t s = k == 0 ? st : tc->st2[k - 1];
+        if (k > 0) AASIST_CUDA(cudaStreamWaitEvent(s, tc->ev_fork, 0));
+        if ((rc = run_range(b0, u0, n, s))) return rc;
+        if (k > 0) AASIST_CUDA(cudaEventRecord(tc->ev_join[k - 1], s));
+        u0 += n;
+      }
+      for (int k = 0; k < n_streams - 1; ++k) AASIST_CUDA(cudaStreamWaitEvent(st, tc->ev_join[k], 0));
     } else if ((rc = run_range(b0, 0, nb, st))) {
       return rc;
     }

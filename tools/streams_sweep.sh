@@ -1,6 +1,6 @@
 #!/bin/bash
 # usage (on the GPU box): tools/streams_sweep.sh [bench args]  -- step throughput with an encoder pass on one / two streams
-for v in 1 2 1 2; do AASIST_TC_STREAMS=$v python bench.py --no-cpu-baseline --no-eager-baseline "$@" 2>/dev/null | python -c "
+for v in ${STREAMS:-1 2 1 2}; do AASIST_TC_STREAMS=$v python bench.py --no-cpu-baseline --no-eager-baseline "$@" 2>/dev/null | python -c "
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):
