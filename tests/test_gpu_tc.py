@@ -173,7 +173,9 @@ def test_tc_larger_batch_crosses_chunk_boundary():
 @pytest.mark.parametrize("B,L", [(1, 64600), (5, 2400), (3, 16001), (7, 30011), (130, 9000), (2, 131072),
                                  # block 0 works on 120-column strips of four 30-column quadrants with their own
                                  # halo rows: widths whose pooled length J0 sits on / next to a strip or quadrant edge
-                                 (2, 3368), (2, 3371), (3, 3377), (2, 3380), (2, 4178), (3, 4190), (2, 6608)])
+                                 (2, 3368), (2, 3371), (3, 3377), (2, 3380), (2, 4178), (3, 4190), (2, 6608),
+                                 # the two halves of an encoder pass run on two streams from 64 utterances on
+                                 (63, 5000), (64, 5000), (65, 9000)])
 def test_tc_path_agrees_with_fp32_path_on_odd_shapes(B, L):
     """Strip/tile edge handling (partial strips, J not a multiple of 120/126/128, tiny widths in the last blocks,
     batch sizes around the CTA count): the tensor-core path against the CUDA-core fp32 path, which the other
